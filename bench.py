@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the Smart-MC hot path on B200, with the FP64 roofline and the CPU baseline.
+
+Workload (BASELINE.json configs[2]): 8192 independent chains x N=256 LJ molecules above the wall,
+main.c geometry (L=33, Lz=240, T=1.1, A=T, M=3), fcc start lattice of initializeBox, PER GPU
+(weak scaling: chains shard across ranks with no data-path collective; only the observable block
+is all-reduced).  One "step" = `sweeps_per_step` sweeps (oneParticleMoves, SMC.c:278-351) of every
+chain in one kernel launch, followed by one gather of the observables (+ the NCCL all-reduce of the
+observable block when N>1).  sweeps_per_step defaults to 40 = the reference's own gather cadence
+(main.c:15-18: 16e6 steps / 4e5 samples).
+
+Metric: pair-interactions/s (one ORDERED (i,j) geometry + LJ energy + force evaluation; a sweep is
+2*N*(N-1) of them); chain-steps/s (sweeps/s) is reported beside it.
+
+  value     device-resident throughput, timed with CUDA events on the engine's launch stream
+  e2e       the same through the public C-ABI with HOST buffers: upload positions, sweeps, gather,
+            download positions + chain state, every step
+  roofline  FP64-pipe bound (the pair kernel is compute bound: ~3.3 MFLOP per 12 KB of state):
+            achieved = (17*pairs + 16*pairs_in_cutoff) flops / kernel time, peak = DFMA peak
+            measured live by smcb_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref, compiled from
+            /root/reference by oracle/build_ref.sh) running oneParticleMoves on all host cores,
+            one independent chain per core - the only parallel mode the reference has.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_PART, M_SITES, L_BOX, LZ_BOX, TEMP = 256, 3, 33.0, 240.0, 1.1
+FLOPS_PAIR, FLOPS_INCUT = 17.0, 16.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="smcb200", choices=["smcb200", "reference"])
+    ap.add_argument("--chains", type=int, default=8192, help="chains per GPU")
+    ap.add_argument("--sweeps-per-step", type=int, default=40)
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--kernel", default="sweep", choices=["sweep", "allparticle"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _ref_worker(args):
+    """one host core = one independent chain of the compiled reference (oracle/_ref)"""
+    libname, nsweeps, seed = args
+    from oracle_bindings import GOLDEN_W_M3, RefLib
+    ref = RefLib(N_PART, M_SITES, fast=libname.endswith("_fast"))
+    R = ref.initializeBox(L_BOX, LZ_BOX)
+    W = GOLDEN_W_M3.copy()
+    ref.lib.oracle_srand(seed)
+    Rn = np.zeros_like(R)
+    j = ctypes.c_int(0)
+    e = ctypes.c_double(0.0)
+    t0 = time.perf_counter()
+    for _ in range(nsweeps):
+        ref.lib.oneParticleMoves(R, Rn, W, L_BOX, LZ_BOX, TEMP, TEMP, ctypes.byref(j), ctypes.byref(e))
+    return time.perf_counter() - t0, j.value
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_steps(pool, cores, nsweeps, nsteps, fast=False):
+    """nsteps x (every core runs nsweeps sweeps of its own chain); returns wall seconds per step"""
+    lib = "ref_fast" if fast else "ref"
+    times = []
+    for s in range(nsteps):
+        t0 = time.perf_counter()
+        pool.map(_ref_worker, [(lib, nsweeps, 1000 * s + c) for c in range(cores)])
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def pairs_per_sweep(n):
+    return 2.0 * n * (n - 1)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref_so = os.path.join(ROOT, "oracle", "_ref", f"libref_N{N_PART}_M{M_SITES}.so")
+    if not os.path.exists(ref_so):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)"}))
+        return
+    cores = host_cores()
+    nsweeps = max(1, min(args.sweeps_per_step, 40))
+    with mp.get_context("fork").Pool(cores) as pool:
+        run_reference_steps(pool, cores, 2, max(1, min(args.warmup, 3)))
+        times = run_reference_steps(pool, cores, nsweeps, args.steps)
+    total = sum(times)
+    sweeps = cores * nsweeps * args.steps
+    value = sweeps * pairs_per_sweep(N_PART) / total
+    line = {
+        "impl": "reference", "metric": "pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
+        "chain_steps_per_s": sweeps / total, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"reference oneParticleMoves (SMC.c:278-351), N={N_PART} wall, one chain per host core",
+                   "N": N_PART, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": TEMP,
+                   "sweeps_per_step": nsweeps, "chains": cores},
+        "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": cores, "kind": "reference",
+                         "sample": f"{cores} chains x {nsweeps} sweeps x {args.steps} steps, gcc -O2 -ffp-contract=off build of /root/reference"},
+        "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(args):
+    """bounded sample of the reference on all host cores (rank 0, N=1 only)"""
+    ref_so = os.path.join(ROOT, "oracle", "_ref", f"libref_N{N_PART}_M{M_SITES}.so")
+    if not os.path.exists(ref_so):
+        return None
+    cores = host_cores()
+    out = {}
+    with mp.get_context("fork").Pool(cores) as pool:
+        for fast in (False, True):
+            run_reference_steps(pool, cores, 2, 1, fast)
+            t_probe = run_reference_steps(pool, cores, 10, 1, fast)[0]
+            nsweeps = int(max(10, min(4000, 10 * (args.cpu_seconds / 2) / max(t_probe, 1e-3))))
+            t = run_reference_steps(pool, cores, nsweeps, 1, fast)[0]
+            out["fast" if fast else "parity"] = (cores * nsweeps / t, nsweeps, t)
+    sps, nsw, t = out["parity"]
+    return {"value": sps * pairs_per_sweep(N_PART), "unit": "pair-interactions/s", "cores": cores, "kind": "reference",
+            "chain_steps_per_s": sps, "chain_steps_per_s_per_core": sps / cores,
+            "sample": f"{cores} host cores x 1 chain x {nsw} sweeps of oneParticleMoves (N={N_PART}, wall), {t:.1f} s, "
+                      "reference compiled -O2 -ffp-contract=off",
+            "courtesy_O3_avx2_value": out["fast"][0] * pairs_per_sweep(N_PART)}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    smcb = importlib.import_module("montecarlo-surfacer_b200")
+    from oracle_bindings import GOLDEN_W_M3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; smcb200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    Cn, N, S = args.chains, N_PART, args.sweeps_per_step
+    mode = smcb.STRICT if args.mode == "strict" else smcb.FAST
+    A = TEMP if args.kernel == "sweep" else 2e-4
+
+    # start lattice of initializeBox(33, 240, 256) (SMC.c:413-465): 4x4x4 fcc cells, a = 8.25, shifted a/4
+    a = L_BOX / 4
+    cells = np.array([(i, j, k) for i in range(4) for j in range(4) for k in range(4)], dtype=float)
+    basis = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]])
+    X = (cells[:, None, :] + basis[None, :, :]).reshape(-1, 3) * a + a / 4
+    Pz = LZ_BOX - LZ_BOX / 20.0
+    X[:, :2] -= L_BOX * np.rint(X[:, :2] / L_BOX)
+    X[:, 2] -= Pz * np.rint(X[:, 2] / Pz)
+    R0 = X.reshape(-1)
+
+    eng = smcb.Engine(Cn, N, M_SITES, device=local)
+    eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=A), GOLDEN_W_M3, ngroups=1)
+    eng.obs_configure(nebins=64, e_lo=-8.0, e_hi=2.0)
+    eng.broadcast_positions(R0)
+    eng.set_rng(12345, rank * Cn, 0)
+    info = eng.device_info()
+    lay = eng.obs_layout()
+
+    obs_cnt = torch.zeros(lay.u64_total, dtype=torch.int64, device="cuda")
+    obs_mom = torch.zeros(lay.f64_total, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def run_kernel():
+        if args.kernel == "sweep":
+            eng.sweep(S, mode)
+        else:
+            eng.step_allparticle(S, mode)
+        return eng.last_kernel_ms()[0]
+
+    def allreduce_obs():
+        """the ONLY collective of the path: sum the observable block over ranks (NCCL)"""
+        if world == 1:
+            return 0.0
+        eng.obs_export_device(obs_cnt.data_ptr(), obs_mom.data_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(obs_cnt)
+        dist.all_reduce(obs_mom)
+        e1.record()
+        torch.cuda.synchronize()
+        eng.obs_reset()          # ranks keep accumulating deltas; the reduced block lives in obs_cnt/obs_mom
+        return e0.elapsed_time(e1)
+
+    def one_step():
+        k_ms = run_kernel()
+        pairs = eng.last_pair_counts()
+        eng.gather()
+        g_ms = eng.last_kernel_ms()[0]
+        c_ms = allreduce_obs()
+        return k_ms, g_ms, c_ms, pairs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak, _ = eng.measure_fp64_peak()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    k_tot = g_tot = c_tot = 0.0
+    pairs_tot = pairs_cut = 0
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        k_ms, g_ms, c_ms, pairs = one_step()
+        k_tot += k_ms; g_tot += g_ms; c_tot += c_ms
+        pairs_tot += pairs[0]; pairs_cut += pairs[1]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+
+    dev_ms = k_tot + g_tot + c_tot
+    if dist is not None:
+        t = torch.tensor([dev_ms, k_tot], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, k_max = t.tolist()
+    else:
+        k_max = k_tot
+    unit_pairs = pairs_per_sweep(N) if args.kernel == "sweep" else float(N) * (N - 1)
+    chain_steps = float(world) * Cn * S * args.steps
+    value = chain_steps * unit_pairs / (dev_ms * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers (every rank, max over ranks) ----------
+    e2e = None
+    if not args.no_e2e:
+        host_R = torch.empty((Cn, 3 * N), dtype=torch.float64).pin_memory().numpy()
+        eng.get_positions(host_R)
+        nsteps_e2e = max(3, min(args.steps, 5))
+
+        def e2e_step():
+            eng.set_positions(host_R)                  # H2D of the step's inputs
+            run_kernel()
+            eng.gather()
+            allreduce_obs()
+            eng.get_positions(host_R)                  # D2H of the step's results
+            return eng.chain_state()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps_e2e):
+            e2e_step()
+        barrier()
+        te = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([te], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = t.item()
+        e2e = {"value": float(world) * Cn * S * nsteps_e2e * unit_pairs / te, "unit": "pair-interactions/s",
+               "chain_steps_per_s": float(world) * Cn * S * nsteps_e2e / te, "steps": nsteps_e2e,
+               "h2d_bytes_per_step": int(Cn * 3 * N * 8), "d2h_bytes_per_step": int(Cn * 3 * N * 8 + Cn * 24),
+               "timing": "host wall clock around set_positions -> kernel -> gather -> get_positions -> chain_state"}
+
+    if rank == 0:
+        flops = FLOPS_PAIR * pairs_tot + FLOPS_INCUT * pairs_cut
+        achieved = flops / (k_tot * 1e-3) / 1e12
+        line = {
+            "metric": "pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
+            "chain_steps_per_s": chain_steps / (dev_ms * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{Cn} chains/GPU x N={N} with wall (BASELINE configs[2]), {args.kernel} kernel, {args.mode}",
+                       "chains_per_gpu": Cn, "N": N, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": A,
+                       "sweeps_per_step": S, "start": "initializeBox fcc lattice + warm-up steps",
+                       "l2": "flushed between timed steps (256 MB write)", "rng": "Philox4x32-10",
+                       "parallelism": f"chains sharded x{world}, NCCL all-reduce of the observable block only"},
+            "kernel_ms_per_step": k_max / args.steps, "gather_ms_per_step": g_tot / args.steps,
+            "allreduce_ms_per_step": c_tot / args.steps, "wall_s_timed_region": t_wall,
+            "pairs_in_cutoff_frac": pairs_cut / max(1, pairs_tot),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None,
+                         "note": "algorithmic flops = 17/ordered pair + 16 more inside the cutoff (SURVEY §8d); peak = DFMA "
+                                 "peak measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); FP64-pipe "
+                                 "utilisation from ncu is in profiles/"},
+            "clocks": clocks, "gpu_launches": args.steps * 3, "device": info,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(args)
+            if cb:
+                line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,654 @@
+// engine.cu — the C ABI of include/smcb200.h over the kernels in kernels.cuh.
+//
+// One smcb_engine owns one CUDA stream and every device buffer of a chain batch.
+// Host buffers cross the boundary in the reference's layouts (AoS double[3N] per
+// chain, SMC.h:84); the AoS<->SoA transposes run on the device.  There is no CPU
+// fallback anywhere in this file: every entry point either launches the sm_100a
+// kernels or returns an error.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+
+using namespace smcb;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SMCB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct smcb_engine {
+    int device = 0, C = 0, N = 0, Npad = 0, M = 0, nwalls = 0, ngroups = 1, nparams = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf<smcb_chain_params> params;
+    DevBuf<double> W, pos, E, stage, F, Fn, dl, e_lj, f_lj, e_wall, f_wall, totals, moments, peak_out;
+    DevBuf<double> fed_a, fed_b;            // host-fed random inputs
+    DevBuf<long long> nacc, ntri, fed_off;
+    DevBuf<unsigned long long> pairs, counters;
+    DevBuf<unsigned char> fed_acc;
+    DevBuf<int> rbin;
+    uint64_t seed = 0x5eed5eedull, step = 0;
+    uint32_t chain0 = 0;
+    double step_scale = 1.0;
+    bool have_params = false, have_pos = false, energy_valid = false, forces_valid = false;
+    int nebins = 64;
+    double e_lo = -8.0, e_hi = 2.0;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    unsigned long long last_pairs[2] = {0, 0};
+
+    DevChains chains()
+    {
+        DevChains d;
+        d.C = C; d.N = N; d.Npad = Npad; d.M = M;
+        d.params = params.p; d.nparams = nparams; d.W = W.p; d.pos = pos.p; d.E = E.p;
+        d.nacc = nacc.p; d.ntri = ntri.p; d.step_scale = step_scale; d.pair_counts = pairs.p;
+        return d;
+    }
+    size_t u64_per_group() const { return (size_t)2 * SMCB_NCX * SMCB_NCX * SMCB_NCZ + SMCB_NCZ + nebins + 1; }
+    size_t f64_per_group() const { return 5; }
+};
+
+static int check(smcb_engine *e)
+{
+    if (!e) return fail(SMCB_ERR_ARG, "null engine");
+    cudaError_t err = cudaSetDevice(e->device);
+    if (err != cudaSuccess) return fail(SMCB_ERR_CUDA, "cudaSetDevice(%d): %s", e->device, cudaGetErrorString(err));
+    return SMCB_OK;
+}
+
+static int need_ready(smcb_engine *e)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->have_params) return fail(SMCB_ERR_STATE, "smcb_set_params has not been called");
+    if (!e->have_pos) return fail(SMCB_ERR_STATE, "smcb_set_positions has not been called");
+    return SMCB_OK;
+}
+
+extern "C" {
+
+const char *smcb_last_error(void) { return g_err.c_str(); }
+
+int smcb_create(smcb_engine **out, int device, int nchains, int N, int M)
+{
+    if (!out) return fail(SMCB_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (nchains <= 0 || N <= 1 || M <= 0) return fail(SMCB_ERR_ARG, "need nchains>0, N>1, M>0 (got %d, %d, %d)", nchains, N, M);
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0)
+        return fail(SMCB_ERR_NODEVICE, "no CUDA device (%s); libsmcb200 has no CPU path", err == cudaSuccess ? "count=0" : cudaGetErrorString(err));
+    if (device < 0 || device >= ndev) return fail(SMCB_ERR_ARG, "device %d out of range (%d present)", device, ndev);
+    CK(cudaSetDevice(device));
+    smcb_engine *e = new (std::nothrow) smcb_engine();
+    if (!e) return fail(SMCB_ERR_ARG, "out of host memory");
+    e->device = device; e->C = nchains; e->N = N; e->Npad = ((N + 31) / 32) * 32; e->M = M;
+    const size_t cn = (size_t)nchains * e->Npad;
+    cudaError_t a = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (a == cudaSuccess) a = cudaEventCreate(&e->ev0);
+    if (a == cudaSuccess) a = cudaEventCreate(&e->ev1);
+    if (a == cudaSuccess) a = e->pos.ensure(3 * cn);
+    if (a == cudaSuccess) a = e->E.ensure(nchains);
+    if (a == cudaSuccess) a = e->nacc.ensure(nchains);
+    if (a == cudaSuccess) a = e->ntri.ensure(nchains);
+    if (a == cudaSuccess) a = e->pairs.ensure(2);
+    if (a == cudaSuccess) a = e->totals.ensure((size_t)4 * nchains);
+    if (a == cudaSuccess) a = e->rbin.ensure((size_t)nchains * N);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->E.p, 0, nchains * sizeof(double), e->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->nacc.p, 0, nchains * sizeof(long long), e->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->ntri.p, 0, nchains * sizeof(long long), e->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->rbin.p, 0, (size_t)nchains * N * sizeof(int), e->stream);
+    if (a == cudaSuccess) a = cudaStreamSynchronize(e->stream);
+    if (a != cudaSuccess) {
+        int rc = fail(SMCB_ERR_CUDA, "smcb_create: %s", cudaGetErrorString(a));
+        smcb_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return SMCB_OK;
+}
+
+int smcb_destroy(smcb_engine *e)
+{
+    if (!e) return SMCB_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->params.release(); e->W.release(); e->pos.release(); e->E.release(); e->stage.release();
+    e->F.release(); e->Fn.release(); e->dl.release(); e->e_lj.release(); e->f_lj.release();
+    e->e_wall.release(); e->f_wall.release(); e->totals.release(); e->moments.release();
+    e->peak_out.release(); e->fed_a.release(); e->fed_b.release(); e->nacc.release(); e->ntri.release();
+    e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return SMCB_OK;
+}
+
+int smcb_device_info(smcb_engine *e, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, e->device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+    return SMCB_OK;
+}
+
+static int obs_alloc(smcb_engine *e)
+{
+    CK(e->counters.ensure(e->u64_per_group() * e->ngroups));
+    CK(e->moments.ensure(e->f64_per_group() * e->ngroups));
+    CK(cudaMemsetAsync(e->counters.p, 0, e->u64_per_group() * e->ngroups * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->moments.p, 0, e->f64_per_group() * e->ngroups * sizeof(double), e->stream));
+    CK(cudaMemsetAsync(e->rbin.p, 0, (size_t)e->C * e->N * sizeof(int), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_set_params(smcb_engine *e, const smcb_chain_params *p, int nparams, const double *W, int nwalls, int ngroups)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!p || (nparams != 1 && nparams != e->C)) return fail(SMCB_ERR_ARG, "nparams must be 1 or nchains (%d), got %d", e->C, nparams);
+    if (ngroups <= 0) return fail(SMCB_ERR_ARG, "ngroups must be positive");
+    bool any_wall = false;
+    for (int i = 0; i < nparams; i++) {
+        if (!(p[i].L > 0) || !(p[i].Lz > 0) || !(p[i].T > 0) || !(p[i].A > 0) || !(p[i].rc2 > 0))
+            return fail(SMCB_ERR_ARG, "chain %d: L, Lz, T, A, rc2 must be positive", i);
+        if (p[i].flags & SMCB_WALL) {
+            any_wall = true;
+            if ((int)p[i].wall >= nwalls) return fail(SMCB_ERR_ARG, "chain %d: wall table %u >= nwalls %d", i, p[i].wall, nwalls);
+        }
+        if ((int)p[i].group >= ngroups) return fail(SMCB_ERR_ARG, "chain %d: group %u >= ngroups %d", i, p[i].group, ngroups);
+    }
+    if (any_wall && (!W || nwalls <= 0)) return fail(SMCB_ERR_ARG, "SMCB_WALL chains need W and nwalls>0");
+    CK(e->params.ensure(nparams));
+    CK(cudaMemcpyAsync(e->params.p, p, nparams * sizeof(*p), cudaMemcpyHostToDevice, e->stream));
+    const size_t wlen = (size_t)(nwalls > 0 ? nwalls : 1) * 2 * e->M * e->M;
+    CK(e->W.ensure(wlen));
+    CK(cudaMemsetAsync(e->W.p, 0, wlen * sizeof(double), e->stream));
+    if (W && nwalls > 0) CK(cudaMemcpyAsync(e->W.p, W, wlen * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->nparams = nparams; e->nwalls = nwalls; e->ngroups = ngroups;
+    e->have_params = true; e->energy_valid = false; e->forces_valid = false;
+    return obs_alloc(e);
+}
+
+int smcb_set_positions(smcb_engine *e, const double *R)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!R) return fail(SMCB_ERR_ARG, "R is null");
+    const size_t n = (size_t)e->C * 3 * e->N;
+    CK(e->stage.ensure(n));
+    CK(cudaMemcpyAsync(e->stage.p, R, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(launch_aos_to_soa(e->stage.p, e->pos.p, e->C, e->N, e->Npad, 3, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->have_pos = true; e->energy_valid = false; e->forces_valid = false;
+    return SMCB_OK;
+}
+
+int smcb_broadcast_positions(smcb_engine *e, const double *R0)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!R0) return fail(SMCB_ERR_ARG, "R0 is null");
+    const size_t one = (size_t)3 * e->N;
+    CK(e->stage.ensure(one * e->C));
+    CK(cudaMemcpyAsync(e->stage.p, R0, one * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    // doubling copies on the device
+    for (size_t have = 1; have < (size_t)e->C;) {
+        const size_t take = (have * 2 <= (size_t)e->C) ? have : (size_t)e->C - have;
+        CK(cudaMemcpyAsync(e->stage.p + have * one, e->stage.p, take * one * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+        have += take;
+    }
+    CK(launch_aos_to_soa(e->stage.p, e->pos.p, e->C, e->N, e->Npad, 3, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->have_pos = true; e->energy_valid = false; e->forces_valid = false;
+    return SMCB_OK;
+}
+
+int smcb_get_positions(smcb_engine *e, double *R)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!R) return fail(SMCB_ERR_ARG, "R is null");
+    if (!e->have_pos) return fail(SMCB_ERR_STATE, "no positions set");
+    const size_t n = (size_t)e->C * 3 * e->N;
+    CK(e->stage.ensure(n));
+    CK(launch_soa_to_aos(e->pos.p, e->stage.p, e->C, e->N, e->Npad, 3, e->stream));
+    CK(cudaMemcpyAsync(R, e->stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_set_rng(smcb_engine *e, uint64_t seed, uint32_t chain0, uint64_t step0)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    e->seed = seed; e->chain0 = chain0; e->step = step0;
+    return SMCB_OK;
+}
+
+int smcb_set_step_scale(smcb_engine *e, double scale)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!(scale > 0)) return fail(SMCB_ERR_ARG, "scale must be positive");
+    e->step_scale = scale;
+    return SMCB_OK;
+}
+
+// --------------------------------------------------------------- evaluation
+static int run_evaluate(smcb_engine *e, int mode, const EvalOut &o)
+{
+    DevChains d = e->chains();
+    d.step_scale = 1.0;
+    d.pair_counts = nullptr;
+    CK(mode == SMCB_STRICT ? launch_evaluate_strict(d, o, e->stream) : launch_evaluate_fast(d, o, e->stream));
+    return SMCB_OK;
+}
+
+static int fetch(smcb_engine *e, const double *soa, double *host, int ncomp)
+{
+    const size_t n = (size_t)e->C * e->N * ncomp;
+    CK(e->stage.ensure((size_t)e->C * 3 * e->N));
+    CK(launch_soa_to_aos(soa, e->stage.p, e->C, e->N, e->Npad, ncomp, e->stream));
+    CK(cudaMemcpyAsync(host, e->stage.p, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_evaluate(smcb_engine *e, int mode, double *e_lj, double *f_lj, double *e_wall, double *f_wall,
+                  double *U_lj, double *U_wall, double *vir_lj, double *vir_wall_ref)
+{
+    int rc = need_ready(e);
+    if (rc) return rc;
+    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
+    const size_t cn = (size_t)e->C * e->Npad;
+    EvalOut o{};
+    if (e_lj) { CK(e->e_lj.ensure(cn)); o.e_lj = e->e_lj.p; }
+    if (f_lj) { CK(e->f_lj.ensure(3 * cn)); o.f_lj = e->f_lj.p; }
+    if (e_wall) { CK(e->e_wall.ensure(cn)); o.e_wall = e->e_wall.p; }
+    if (f_wall) { CK(e->f_wall.ensure(3 * cn)); o.f_wall = e->f_wall.p; }
+    o.totals = e->totals.p;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if ((rc = run_evaluate(e, mode, o))) return rc;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    e->last_launches = 1;
+    if (e_lj && (rc = fetch(e, o.e_lj, e_lj, 1))) return rc;
+    if (f_lj && (rc = fetch(e, o.f_lj, f_lj, 3))) return rc;
+    if (e_wall && (rc = fetch(e, o.e_wall, e_wall, 1))) return rc;
+    if (f_wall && (rc = fetch(e, o.f_wall, f_wall, 3))) return rc;
+    if (U_lj || U_wall || vir_lj || vir_wall_ref) {
+        std::vector<double> t((size_t)4 * e->C);
+        CK(cudaMemcpyAsync(t.data(), e->totals.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        for (int c = 0; c < e->C; c++) {
+            if (U_lj) U_lj[c] = t[4 * c];
+            if (U_wall) U_wall[c] = t[4 * c + 1];
+            if (vir_lj) vir_lj[c] = t[4 * c + 2];
+            if (vir_wall_ref) vir_wall_ref[c] = t[4 * c + 3];
+        }
+    }
+    return SMCB_OK;
+}
+
+// E <- energy(R) + wallsEnergy(R)   (SMC.c:48)
+static int refresh_energy(smcb_engine *e, int mode)
+{
+    EvalOut o{};
+    o.totals = e->totals.p;
+    int rc = run_evaluate(e, mode, o);
+    if (rc) return rc;
+    // E[c] = totals[4c] + totals[4c+1]: strided 2-D copies then an add would need a kernel;
+    // C is small next to a sweep, do it through the host once.
+    std::vector<double> t((size_t)4 * e->C), E(e->C);
+    CK(cudaMemcpyAsync(t.data(), e->totals.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < e->C; c++) E[c] = t[4 * c] + t[4 * c + 1];
+    CK(cudaMemcpyAsync(e->E.p, E.data(), E.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->energy_valid = true;
+    return SMCB_OK;
+}
+
+int smcb_refresh_energy(smcb_engine *e, int mode)
+{
+    int rc = need_ready(e);
+    if (rc) return rc;
+    return refresh_energy(e, mode);
+}
+
+int smcb_get_chain_state(smcb_engine *e, double *E, int64_t *naccept, int64_t *ntrials)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (E) CK(cudaMemcpyAsync(E, e->E.p, e->C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (naccept) CK(cudaMemcpyAsync(naccept, e->nacc.p, e->C * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    if (ntrials) CK(cudaMemcpyAsync(ntrials, e->ntri.p, e->C * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_reset_counters(smcb_engine *e)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(e->nacc.p, 0, e->C * sizeof(long long), e->stream));
+    CK(cudaMemsetAsync(e->ntri.p, 0, e->C * sizeof(long long), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+// -------------------------------------------------------------------- sweep
+static int finish_timed(smcb_engine *e, int launches)
+{
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(e->last_pairs, e->pairs.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    e->last_launches = launches;
+    return SMCB_OK;
+}
+
+static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const double *displ,
+                        const int64_t *offset, const double *u, uint8_t *accepted)
+{
+    int rc = need_ready(e);
+    if (rc) return rc;
+    if (nsweeps < 0) return fail(SMCB_ERR_ARG, "nsweeps < 0");
+    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
+    if (e->N > kSweepMaxN) return fail(SMCB_ERR_ARG, "sweep kernel supports N <= %d (N = %d): use smcb_step_allparticle", kSweepMaxN, e->N);
+    if (nsweeps == 0) return SMCB_OK;
+    if (!e->energy_valid && (rc = refresh_energy(e, mode))) return rc;
+    SweepArgs a{};
+    a.nsweeps = nsweeps;
+    a.rng = RngArgs{(uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->chain0, e->step};
+    const size_t sc = (size_t)nsweeps * e->C;
+    if (fed) {
+        if (!displ || !offset || !u) return fail(SMCB_ERR_ARG, "fed sweep needs displ, offset and u");
+        CK(e->fed_a.ensure(sc * 3 * e->N));
+        CK(e->fed_b.ensure(sc * e->N));
+        CK(e->fed_off.ensure(sc));
+        CK(cudaMemcpyAsync(e->fed_a.p, displ, sc * 3 * e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->fed_b.p, u, sc * e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->fed_off.p, offset, sc * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+        a.displ = e->fed_a.p; a.u = e->fed_b.p; a.offset = e->fed_off.p;
+        if (accepted) { CK(e->fed_acc.ensure(sc * e->N)); a.accepted = e->fed_acc.p; }
+    }
+    CK(cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    const DevChains d = e->chains();
+    CK(mode == SMCB_STRICT ? launch_sweep_strict(fed, d, a, e->stream) : launch_sweep_fast(fed, d, a, e->stream));
+    if ((rc = finish_timed(e, 1))) return rc;
+    if (fed && accepted) {
+        CK(cudaMemcpyAsync(accepted, e->fed_acc.p, sc * e->N, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    if (!fed) e->step += (uint64_t)nsweeps;
+    e->forces_valid = false;
+    return SMCB_OK;
+}
+
+int smcb_sweep_fed(smcb_engine *e, int nsweeps, int mode, const double *displ, const int64_t *offset,
+                   const double *u, uint8_t *accepted)
+{
+    return sweep_common(e, nsweeps, mode, true, displ, offset, u, accepted);
+}
+
+int smcb_sweep(smcb_engine *e, int nsweeps, int mode)
+{
+    return sweep_common(e, nsweeps, mode, false, nullptr, nullptr, nullptr, nullptr);
+}
+
+// ------------------------------------------------------- all-particle step
+static int step_common(smcb_engine *e, int nsteps, int mode, bool fed, const double *xi, const double *u,
+                       double *lnap, uint8_t *accepted)
+{
+    int rc = need_ready(e);
+    if (rc) return rc;
+    if (nsteps < 0) return fail(SMCB_ERR_ARG, "nsteps < 0");
+    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
+    if ((size_t)(6 * e->Npad + 256) * sizeof(double) > 227 * 1024)
+        return fail(SMCB_ERR_ARG, "N = %d does not fit one CTA's shared memory", e->N);
+    if (nsteps == 0) return SMCB_OK;
+    const size_t cn3 = (size_t)e->C * 3 * e->Npad;
+    CK(e->F.ensure(cn3)); CK(e->Fn.ensure(cn3)); CK(e->dl.ensure(cn3));
+    StepArgs a{};
+    a.nsteps = nsteps;
+    a.refresh = (e->forces_valid && e->energy_valid) ? 0 : 1;
+    a.rng = RngArgs{(uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->chain0, e->step};
+    a.F = e->F.p; a.Fn = e->Fn.p; a.dl = e->dl.p;
+    const size_t sc = (size_t)nsteps * e->C;
+    if (fed) {
+        if (!xi || !u) return fail(SMCB_ERR_ARG, "fed step needs xi and u");
+        CK(e->fed_a.ensure(sc * 3 * e->N));
+        CK(e->fed_b.ensure(sc));
+        CK(cudaMemcpyAsync(e->fed_a.p, xi, sc * 3 * e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->fed_b.p, u, sc * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        a.xi = e->fed_a.p; a.u = e->fed_b.p;
+    }
+    if (lnap) { CK(e->stage.ensure(sc > (size_t)e->C * 3 * e->N ? sc : (size_t)e->C * 3 * e->N)); a.lnap = e->stage.p; }
+    if (accepted) { CK(e->fed_acc.ensure(sc)); a.accepted = e->fed_acc.p; }
+    CK(cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    const DevChains d = e->chains();
+    CK(mode == SMCB_STRICT ? launch_allparticle_strict(fed, d, a, e->stream) : launch_allparticle_fast(fed, d, a, e->stream));
+    if ((rc = finish_timed(e, 1))) return rc;
+    if (lnap) CK(cudaMemcpyAsync(lnap, a.lnap, sc * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (accepted) CK(cudaMemcpyAsync(accepted, a.accepted, sc, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (!fed) e->step += (uint64_t)nsteps;
+    e->forces_valid = true; e->energy_valid = true;
+    return SMCB_OK;
+}
+
+int smcb_step_allparticle_fed(smcb_engine *e, int nsteps, int mode, const double *xi, const double *u,
+                              double *lnap, uint8_t *accepted)
+{
+    return step_common(e, nsteps, mode, true, xi, u, lnap, accepted);
+}
+
+int smcb_step_allparticle(smcb_engine *e, int nsteps, int mode)
+{
+    return step_common(e, nsteps, mode, false, nullptr, nullptr, nullptr, nullptr);
+}
+
+// -------------------------------------------------------------- observables
+int smcb_obs_configure(smcb_engine *e, int nebins, double e_lo, double e_hi)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (nebins <= 0 || !(e_hi > e_lo)) return fail(SMCB_ERR_ARG, "need nebins>0 and e_hi>e_lo");
+    e->nebins = nebins; e->e_lo = e_lo; e->e_hi = e_hi;
+    return obs_alloc(e);
+}
+
+int smcb_obs_layout_get(smcb_engine *e, smcb_obs_layout *out)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!out) return fail(SMCB_ERR_ARG, "out is null");
+    out->ngroups = e->ngroups;
+    out->nvox = SMCB_NCX * SMCB_NCX * SMCB_NCZ;
+    out->nz = SMCB_NCZ;
+    out->nebins = e->nebins;
+    out->e_lo = e->e_lo; out->e_hi = e->e_hi;
+    out->u64_per_group = e->u64_per_group();
+    out->f64_per_group = e->f64_per_group();
+    out->u64_total = e->u64_per_group() * e->ngroups;
+    out->f64_total = e->f64_per_group() * e->ngroups;
+    return SMCB_OK;
+}
+
+int smcb_gather(smcb_engine *e)
+{
+    int rc = need_ready(e);
+    if (rc) return rc;
+    if (!e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");
+    EvalOut o{};
+    o.totals = e->totals.p;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if ((rc = run_evaluate(e, SMCB_FAST, o))) return rc;
+    GatherArgs g{};
+    g.totals = e->totals.p; g.rbin = e->rbin.p; g.counters = e->counters.p; g.moments = e->moments.p;
+    g.u64_per_group = e->u64_per_group(); g.f64_per_group = e->f64_per_group();
+    g.nebins = e->nebins; g.e_lo = e->e_lo; g.e_hi = e->e_hi;
+    CK(launch_gather(e->chains(), g, e->stream));
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    e->last_launches = 2;
+    return SMCB_OK;
+}
+
+int smcb_obs_reset(smcb_engine *e)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    return obs_alloc(e);
+}
+
+int smcb_obs_get(smcb_engine *e, uint64_t *counters, double *moments)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");
+    if (counters) CK(cudaMemcpyAsync(counters, e->counters.p, e->u64_per_group() * e->ngroups * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (moments) CK(cudaMemcpyAsync(moments, e->moments.p, e->f64_per_group() * e->ngroups * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_obs_export_device(smcb_engine *e, void *counters_dev, void *moments_dev)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");
+    if (counters_dev) CK(cudaMemcpyAsync(counters_dev, e->counters.p, e->u64_per_group() * e->ngroups * sizeof(uint64_t), cudaMemcpyDeviceToDevice, e->stream));
+    if (moments_dev) CK(cudaMemcpyAsync(moments_dev, e->moments.p, e->f64_per_group() * e->ngroups * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void *moments_dev)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");
+    if (counters_dev) CK(cudaMemcpyAsync(e->counters.p, counters_dev, e->u64_per_group() * e->ngroups * sizeof(uint64_t), cudaMemcpyDeviceToDevice, e->stream));
+    if (moments_dev) CK(cudaMemcpyAsync(e->moments.p, moments_dev, e->f64_per_group() * e->ngroups * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_get_rbin(smcb_engine *e, int32_t *rbin)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!rbin) return fail(SMCB_ERR_ARG, "rbin is null");
+    CK(cudaMemcpyAsync(rbin, e->rbin.p, (size_t)e->C * e->N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+// -------------------------------------------------------------- measurement
+int smcb_last_kernel_ms(smcb_engine *e, float *ms, int *launches)
+{
+    if (!e) return fail(SMCB_ERR_ARG, "null engine");
+    if (ms) *ms = e->last_ms;
+    if (launches) *launches = e->last_launches;
+    return SMCB_OK;
+}
+
+int smcb_last_pair_counts(smcb_engine *e, uint64_t *pairs_total, uint64_t *pairs_in_cutoff)
+{
+    if (!e) return fail(SMCB_ERR_ARG, "null engine");
+    if (pairs_total) *pairs_total = e->last_pairs[0];
+    if (pairs_in_cutoff) *pairs_in_cutoff = e->last_pairs[1];
+    return SMCB_OK;
+}
+
+int smcb_measure_fp64_peak(smcb_engine *e, double *tflops, float *ms_out)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, e->device));
+    CK(e->peak_out.ensure(1));
+    const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 2048;
+    CK(launch_dfma_peak(e->peak_out.p, blocks, threads, 64, e->stream));       // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e->ev0, e->stream));
+        CK(launch_dfma_peak(e->peak_out.p, blocks, threads, iters, e->stream));
+        CK(cudaEventRecord(e->ev1, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+        if (ms < best) best = ms;
+    }
+    const double flops = (double)blocks * threads * (double)iters * 64.0 * 2.0;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return SMCB_OK;
+}
+
+int smcb_device_positions(smcb_engine *e, void **ptr, size_t *bytes, int *npad)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (ptr) *ptr = e->pos.p;
+    if (bytes) *bytes = (size_t)e->C * 3 * e->Npad * sizeof(double);
+    if (npad) *npad = e->Npad;
+    return SMCB_OK;
+}
+
+void *smcb_stream(smcb_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+}  // extern "C"

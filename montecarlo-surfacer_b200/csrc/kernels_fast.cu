@@ -1,0 +1,39 @@
+// kernels_fast.cu — FAST instantiations (FMA contraction on) plus the kernels
+// that have no strict/fast distinction (gather, layout transposes, DFMA peak).
+#define SMCB_MISC_KERNELS
+#include "launch.h"
+#define SMCB_TU_STRICT false
+#define SMCB_TU_SUFFIX fast
+#include "launchers.inl"
+
+namespace smcb {
+
+cudaError_t launch_gather(const DevChains &d, const GatherArgs &g, cudaStream_t st)
+{
+    k_gather<<<d.C, 128, 0, st>>>(d, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aos_to_soa(const double *aos, double *soa, int C, int N, int Npad, int ncomp, cudaStream_t st)
+{
+    const size_t total = (size_t)C * Npad;
+    const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    k_aos_to_soa<<<blocks ? blocks : 1, 256, 0, st>>>(aos, soa, C, N, Npad, ncomp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_soa_to_aos(const double *soa, double *aos, int C, int N, int Npad, int ncomp, cudaStream_t st)
+{
+    const size_t total = (size_t)C * N;
+    const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    k_soa_to_aos<<<blocks ? blocks : 1, 256, 0, st>>>(soa, aos, C, N, Npad, ncomp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dfma_peak(double *out, int blocks, int threads, int iters, cudaStream_t st)
+{
+    k_dfma_peak<<<blocks, threads, 0, st>>>(out, iters, 1.0);
+    return cudaGetLastError();
+}
+
+}  // namespace smcb

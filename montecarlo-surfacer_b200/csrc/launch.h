@@ -1,0 +1,25 @@
+// launch.h — host-side launch entry points of the two kernel translation units.
+#pragma once
+#include "kernels.cuh"
+
+namespace smcb {
+
+// kernels_fast.cu (FMA contraction on) and kernels_strict.cu (--fmad=false)
+// each define one set; `strict` picks the set at run time in engine.cu.
+#define SMCB_DECLARE_LAUNCHERS(SUFFIX)                                                              \
+    cudaError_t launch_evaluate_##SUFFIX(const DevChains &d, const EvalOut &o, cudaStream_t st);    \
+    cudaError_t launch_sweep_##SUFFIX(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st); \
+    cudaError_t launch_allparticle_##SUFFIX(bool fed, const DevChains &d, const StepArgs &a, cudaStream_t st);
+
+SMCB_DECLARE_LAUNCHERS(fast)
+SMCB_DECLARE_LAUNCHERS(strict)
+
+cudaError_t launch_gather(const DevChains &d, const GatherArgs &g, cudaStream_t st);
+cudaError_t launch_aos_to_soa(const double *aos, double *soa, int C, int N, int Npad, int ncomp, cudaStream_t st);
+cudaError_t launch_soa_to_aos(const double *soa, double *aos, int C, int N, int Npad, int ncomp, cudaStream_t st);
+cudaError_t launch_dfma_peak(double *out, int blocks, int threads, int iters, cudaStream_t st);
+
+// largest N the warp-per-chain sweep kernel is instantiated for
+constexpr int kSweepMaxN = 512;
+
+}  // namespace smcb

@@ -1,0 +1,334 @@
+"""ctypes binding of include/smcb200.h (one Engine = one smcb_engine handle = one GPU).
+
+Method names follow the C entry points; array arguments are numpy arrays in the reference's
+layouts (positions AoS [chain][3N], SMC.h:84; W interleaved (a,b), SMC.c:745-760).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+FAST, STRICT = 0, 1
+WALL, PERIODIC_Z = 1, 2
+A0_DEFAULT = 5.960464477539063e-9   # SMC.h:32
+B0_DEFAULT = 2.44140625e-5          # SMC.h:33
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+
+class SmcbError(RuntimeError):
+    pass
+
+
+class ChainParams(C.Structure):
+    """smcb_chain_params"""
+    _fields_ = [("L", C.c_double), ("Lz", C.c_double), ("T", C.c_double), ("A", C.c_double),
+                ("rc2", C.c_double), ("a0", C.c_double), ("b0", C.c_double),
+                ("flags", C.c_uint32), ("wall", C.c_uint32), ("group", C.c_uint32), ("pad_", C.c_uint32)]
+
+
+class ObsLayout(C.Structure):
+    """smcb_obs_layout"""
+    _fields_ = [("ngroups", C.c_int), ("nvox", C.c_int), ("nz", C.c_int), ("nebins", C.c_int),
+                ("e_lo", C.c_double), ("e_hi", C.c_double),
+                ("u64_per_group", C.c_size_t), ("f64_per_group", C.c_size_t),
+                ("u64_total", C.c_size_t), ("f64_total", C.c_size_t)]
+
+
+def default_params(L=33.0, Lz=240.0, T=1.1, A=None, rc2=9.0, a0=A0_DEFAULT, b0=B0_DEFAULT,
+                   flags=WALL, wall=0, group=0):
+    """main.c geometry (main.c:35-51): L=33, Lz=240 (N>=150), A = gamma*T with gamma=1"""
+    return ChainParams(L, Lz, T, T if A is None else A, rc2, a0, b0, flags, wall, group, 0)
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsmcb200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load libsmcb200.so or fail loudly - there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SmcbError(f"{path} not found: build it with `make -C montecarlo-surfacer_b200/csrc` "
+                        "(or __graft_entry__.build()); smcb200 has no CPU fallback")
+    lib = C.CDLL(path)
+    P = C.c_void_p
+    dp = C.POINTER(C.c_double)
+    sig = {
+        "smcb_create": [C.POINTER(P), C.c_int, C.c_int, C.c_int, C.c_int],
+        "smcb_destroy": [P],
+        "smcb_device_info": [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)],
+        "smcb_set_params": [P, C.POINTER(ChainParams), C.c_int, P, C.c_int, C.c_int],
+        "smcb_set_positions": [P, P],
+        "smcb_get_positions": [P, P],
+        "smcb_broadcast_positions": [P, P],
+        "smcb_set_rng": [P, C.c_uint64, C.c_uint32, C.c_uint64],
+        "smcb_evaluate": [P, C.c_int] + [P] * 8,
+        "smcb_sweep_fed": [P, C.c_int, C.c_int, P, P, P, P],
+        "smcb_sweep": [P, C.c_int, C.c_int],
+        "smcb_set_step_scale": [P, C.c_double],
+        "smcb_step_allparticle_fed": [P, C.c_int, C.c_int, P, P, P, P],
+        "smcb_step_allparticle": [P, C.c_int, C.c_int],
+        "smcb_refresh_energy": [P, C.c_int],
+        "smcb_get_chain_state": [P, P, P, P],
+        "smcb_reset_counters": [P],
+        "smcb_obs_configure": [P, C.c_int, C.c_double, C.c_double],
+        "smcb_obs_layout_get": [P, C.POINTER(ObsLayout)],
+        "smcb_gather": [P],
+        "smcb_obs_reset": [P],
+        "smcb_obs_get": [P, P, P],
+        "smcb_obs_export_device": [P, P, P],
+        "smcb_obs_import_device": [P, P, P],
+        "smcb_get_rbin": [P, P],
+        "smcb_last_kernel_ms": [P, C.POINTER(C.c_float), C.POINTER(C.c_int)],
+        "smcb_last_pair_counts": [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+        "smcb_measure_fp64_peak": [P, dp, C.POINTER(C.c_float)],
+        "smcb_device_positions": [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.smcb_last_error.restype = C.c_char_p
+    lib.smcb_stream.argtypes = [P]
+    lib.smcb_stream.restype = P
+    _lib = lib
+    return lib
+
+
+def header_symbols():
+    """every function name declared in include/smcb200.h"""
+    text = open(os.path.join(_ROOT, "include", "smcb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(smcb_[a-z0-9_]+)\s*\(", text)))
+
+
+def exported_symbols():
+    """dynamic symbols libsmcb200.so exports (via ctypes lookup of the header's names)"""
+    lib = load_library()
+    return [s for s in header_symbols() if hasattr(lib, s)]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} doubles, got {a.size}")
+    return a
+
+
+class Engine:
+    """A batch of `nchains` independent chains of `N` particles on one GPU."""
+
+    def __init__(self, nchains, N, M=3, device=0):
+        self.lib = load_library()
+        self.C, self.N, self.M = int(nchains), int(N), int(M)
+        self._h = C.c_void_p()
+        rc = self.lib.smcb_create(C.byref(self._h), device, self.C, self.N, self.M)
+        if rc != 0:
+            self._h = None
+            raise SmcbError(f"smcb_create failed ({rc}): {self.lib.smcb_last_error().decode()}")
+
+    # -- plumbing ------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise SmcbError(f"smcb error {rc}: {self.lib.smcb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.smcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def device_info(self):
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._ck(self.lib.smcb_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": mem.value}
+
+    # -- inputs --------------------------------------------------------------
+    def set_params(self, params, W=None, ngroups=1):
+        """params: one ChainParams or a sequence of nchains; W: [nwalls][2*M*M]"""
+        if isinstance(params, ChainParams):
+            arr = (ChainParams * 1)(params)
+            n = 1
+        else:
+            params = list(params)
+            n = len(params)
+            arr = (ChainParams * n)(*params)
+        if W is None:
+            Wc, nw = None, 0
+        else:
+            Wc = _f64(W)
+            if Wc.size % (2 * self.M * self.M):
+                raise ValueError("W must hold whole tables of 2*M*M doubles")
+            nw = Wc.size // (2 * self.M * self.M)
+        self._ck(self.lib.smcb_set_params(self._h, arr, n, _ptr(Wc), nw, ngroups))
+
+    def set_positions(self, R):
+        R = _f64(R, self.C * 3 * self.N)
+        self._ck(self.lib.smcb_set_positions(self._h, _ptr(R)))
+
+    def broadcast_positions(self, R0):
+        R0 = _f64(R0, 3 * self.N)
+        self._ck(self.lib.smcb_broadcast_positions(self._h, _ptr(R0)))
+
+    def get_positions(self, out=None):
+        R = np.empty((self.C, 3 * self.N)) if out is None else out
+        self._ck(self.lib.smcb_get_positions(self._h, _ptr(R)))
+        return R
+
+    def set_rng(self, seed, chain0=0, step0=0):
+        self._ck(self.lib.smcb_set_rng(self._h, seed, chain0, step0))
+
+    def set_step_scale(self, scale):
+        self._ck(self.lib.smcb_set_step_scale(self._h, scale))
+
+    # -- static evaluation -----------------------------------------------------
+    def evaluate(self, mode=FAST, per_particle=True):
+        """dict with e_lj[C,N], f_lj[C,3N], e_wall[C,N], f_wall[C,3N] (if per_particle) and the
+        chain totals U_lj, U_wall, vir_lj, vir_wall_ref [C]"""
+        Cn, N = self.C, self.N
+        out = {k: np.empty(Cn) for k in ("U_lj", "U_wall", "vir_lj", "vir_wall_ref")}
+        if per_particle:
+            out.update(e_lj=np.empty((Cn, N)), f_lj=np.empty((Cn, 3 * N)),
+                       e_wall=np.empty((Cn, N)), f_wall=np.empty((Cn, 3 * N)))
+        g = out.get
+        self._ck(self.lib.smcb_evaluate(self._h, mode, _ptr(g("e_lj")), _ptr(g("f_lj")), _ptr(g("e_wall")),
+                                        _ptr(g("f_wall")), _ptr(out["U_lj"]), _ptr(out["U_wall"]),
+                                        _ptr(out["vir_lj"]), _ptr(out["vir_wall_ref"])))
+        return out
+
+    # -- the sweep ---------------------------------------------------------------
+    def sweep_fed(self, displ, offset, u, mode=STRICT, want_accepted=False):
+        """displ [S,C,3N], offset [S,C] (int64), u [S,C,N]"""
+        displ = _f64(displ)
+        S = displ.size // (self.C * 3 * self.N)
+        offset = np.ascontiguousarray(offset, dtype=np.int64)
+        u = _f64(u, S * self.C * self.N)
+        if displ.size != S * self.C * 3 * self.N or offset.size != S * self.C:
+            raise ValueError("fed sweep input shapes do not agree")
+        acc = np.zeros((S, self.C, self.N), dtype=np.uint8) if want_accepted else None
+        self._ck(self.lib.smcb_sweep_fed(self._h, S, mode, _ptr(displ), _ptr(offset), _ptr(u), _ptr(acc)))
+        return acc
+
+    def sweep(self, nsweeps, mode=FAST):
+        self._ck(self.lib.smcb_sweep(self._h, nsweeps, mode))
+
+    # -- the all-particle step -----------------------------------------------------
+    def step_allparticle_fed(self, xi, u, mode=FAST):
+        """xi [S,C,3N] (already scaled by sqrt(2A)), u [S,C]; returns (lnap [S,C], accepted [S,C])"""
+        xi = _f64(xi)
+        S = xi.size // (self.C * 3 * self.N)
+        u = _f64(u, S * self.C)
+        lnap = np.empty((S, self.C))
+        acc = np.zeros((S, self.C), dtype=np.uint8)
+        self._ck(self.lib.smcb_step_allparticle_fed(self._h, S, mode, _ptr(xi), _ptr(u), _ptr(lnap), _ptr(acc)))
+        return lnap, acc
+
+    def step_allparticle(self, nsteps, mode=FAST):
+        self._ck(self.lib.smcb_step_allparticle(self._h, nsteps, mode))
+
+    # -- chain state -------------------------------------------------------------
+    def refresh_energy(self, mode=FAST):
+        self._ck(self.lib.smcb_refresh_energy(self._h, mode))
+
+    def chain_state(self):
+        E = np.empty(self.C)
+        na = np.empty(self.C, dtype=np.int64)
+        nt = np.empty(self.C, dtype=np.int64)
+        self._ck(self.lib.smcb_get_chain_state(self._h, _ptr(E), _ptr(na), _ptr(nt)))
+        return E, na, nt
+
+    def reset_counters(self):
+        self._ck(self.lib.smcb_reset_counters(self._h))
+
+    # -- observables ---------------------------------------------------------------
+    def obs_configure(self, nebins=64, e_lo=-8.0, e_hi=2.0):
+        self._ck(self.lib.smcb_obs_configure(self._h, nebins, e_lo, e_hi))
+
+    def obs_layout(self):
+        lay = ObsLayout()
+        self._ck(self.lib.smcb_obs_layout_get(self._h, C.byref(lay)))
+        return lay
+
+    def gather(self):
+        self._ck(self.lib.smcb_gather(self._h))
+
+    def obs_reset(self):
+        self._ck(self.lib.smcb_obs_reset(self._h))
+
+    def obs_get(self):
+        """returns dict per group index: D, Mu [33,33,33], zprof [33], ehist, nsamples, and moments"""
+        lay = self.obs_layout()
+        cnt = np.zeros(lay.u64_total, dtype=np.uint64)
+        mom = np.zeros(lay.f64_total)
+        self._ck(self.lib.smcb_obs_get(self._h, _ptr(cnt), _ptr(mom)))
+        return unpack_obs(lay, cnt, mom)
+
+    def obs_export_device(self, counters_ptr, moments_ptr):
+        self._ck(self.lib.smcb_obs_export_device(self._h, counters_ptr, moments_ptr))
+
+    def obs_import_device(self, counters_ptr, moments_ptr):
+        self._ck(self.lib.smcb_obs_import_device(self._h, counters_ptr, moments_ptr))
+
+    def rbin(self):
+        rb = np.empty((self.C, self.N), dtype=np.int32)
+        self._ck(self.lib.smcb_get_rbin(self._h, _ptr(rb)))
+        return rb
+
+    # -- measurement -----------------------------------------------------------------
+    def last_kernel_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        self._ck(self.lib.smcb_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def last_pair_counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.smcb_last_pair_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def measure_fp64_peak(self):
+        t, ms = C.c_double(), C.c_float()
+        self._ck(self.lib.smcb_measure_fp64_peak(self._h, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    def stream(self):
+        return self.lib.smcb_stream(self._h)
+
+
+def unpack_obs(lay, cnt, mom):
+    """split the packed observable block (smcb_obs_layout) into named arrays per group"""
+    groups = []
+    nv, nz, ne = lay.nvox, lay.nz, lay.nebins
+    for g in range(lay.ngroups):
+        c = cnt[g * lay.u64_per_group:(g + 1) * lay.u64_per_group]
+        m = mom[g * lay.f64_per_group:(g + 1) * lay.f64_per_group]
+        groups.append({
+            "D": c[:nv].reshape(33, 33, 33), "Mu": c[nv:2 * nv].reshape(33, 33, 33),
+            "zprof": c[2 * nv:2 * nv + nz], "ehist": c[2 * nv + nz:2 * nv + nz + ne],
+            "nsamples": int(c[2 * nv + nz + ne]),
+            "sumE": m[0], "sumE2": m[1], "sumP": m[2], "sumP2": m[3], "sumAcc": m[4],
+        })
+    return groups
