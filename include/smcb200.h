@@ -183,6 +183,12 @@ int smcb_measure_fp64_peak(smcb_engine *e, double *tflops, float *ms);
 /* raw device pointers for the stream-resident benchmark path (positions SoA
  * [chain][3][Npad]) */
 int smcb_device_positions(smcb_engine *e, void **ptr, size_t *bytes, int *npad);
+/* test hook: the FAST sweep kernel keeps per-particle energy / force / neighbour-count caches
+ * (csrc/sweep_cached.cuh).  With capture on, the next FAST smcb_sweep* call leaves them here:
+ * e_tot[c][N] = energySingle + wallsEnergySingle, f_tot[c][3N] = forceSingle + wallsForce,
+ * nb[c][N] = partners inside the cutoff, as the kernel held them after its last trial. */
+int smcb_debug_capture_cache(smcb_engine *e, int on);
+int smcb_debug_get_cache(smcb_engine *e, double *e_tot, double *f_tot, double *nb);
 void *smcb_stream(smcb_engine *e);
 
 #ifdef __cplusplus

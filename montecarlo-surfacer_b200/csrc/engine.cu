@@ -59,6 +59,8 @@ struct smcb_engine {
     DevBuf<smcb_chain_params> params;
     DevBuf<double> W, pos, E, stage, F, Fn, dl, e_lj, f_lj, e_wall, f_wall, totals, moments, peak_out;
     DevBuf<double> fed_a, fed_b;            // host-fed random inputs
+    DevBuf<double> cache_out;               // test hook (smcb_debug_capture_cache)
+    bool capture_cache = false;
     DevBuf<long long> nacc, ntri, fed_off;
     DevBuf<unsigned long long> pairs, counters;
     DevBuf<unsigned char> fed_acc;
@@ -155,7 +157,7 @@ int smcb_destroy(smcb_engine *e)
     e->F.release(); e->Fn.release(); e->dl.release(); e->e_lj.release(); e->f_lj.release();
     e->e_wall.release(); e->f_wall.release(); e->totals.release(); e->moments.release();
     e->peak_out.release(); e->fed_a.release(); e->fed_b.release(); e->nacc.release(); e->ntri.release();
-    e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
+    e->cache_out.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -421,6 +423,10 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
         a.displ = e->fed_a.p; a.u = e->fed_b.p; a.offset = e->fed_off.p;
         if (accepted) { CK(e->fed_acc.ensure(sc * e->N)); a.accepted = e->fed_acc.p; }
     }
+    if (e->capture_cache && mode == SMCB_FAST) {
+        CK(e->cache_out.ensure((size_t)e->C * 5 * e->Npad));
+        a.cache_out = e->cache_out.p;
+    }
     CK(cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     const DevChains d = e->chains();
@@ -646,6 +652,34 @@ int smcb_device_positions(smcb_engine *e, void **ptr, size_t *bytes, int *npad)
     if (ptr) *ptr = e->pos.p;
     if (bytes) *bytes = (size_t)e->C * 3 * e->Npad * sizeof(double);
     if (npad) *npad = e->Npad;
+    return SMCB_OK;
+}
+
+int smcb_debug_capture_cache(smcb_engine *e, int on)
+{
+    if (!e) return fail(SMCB_ERR_ARG, "null engine");
+    e->capture_cache = on != 0;
+    return SMCB_OK;
+}
+
+int smcb_debug_get_cache(smcb_engine *e, double *e_tot, double *f_tot, double *nb)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->cache_out.p) return fail(SMCB_ERR_STATE, "no cache captured (smcb_debug_capture_cache + a FAST sweep first)");
+    const size_t CN = (size_t)e->C * e->N;
+    std::vector<double> h((size_t)e->C * 5 * e->Npad);
+    CK(cudaMemcpyAsync(h.data(), e->cache_out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (size_t c = 0; c < (size_t)e->C; c++) {
+        const double *q = h.data() + c * 5 * e->Npad;
+        for (int j = 0; j < e->N; j++) {
+            if (e_tot) e_tot[c * e->N + j] = q[j];
+            if (f_tot) for (int k = 0; k < 3; k++) f_tot[(c * e->N + j) * 3 + k] = q[(1 + k) * e->Npad + j];
+            if (nb) nb[c * e->N + j] = q[4 * e->Npad + j];
+        }
+    }
+    (void)CN;
     return SMCB_OK;
 }
 

@@ -48,6 +48,7 @@ struct SweepArgs {
     const long long *offset;   // FED: [s][C]
     const double *u;           // FED: [s][C][N]
     unsigned char *accepted;   // FED, nullable: [s][C][N]
+    double *cache_out;         // test hook of the cached kernel, nullable: [C][5][Npad]
 };
 
 struct StepArgs {
@@ -148,6 +149,169 @@ __global__ void k_evaluate(DevChains d, EvalOut o)
 // added one by one in ascending particle index (k-major, lane-minor = l
 // ascending), all lanes keeping identical accumulators.  The surface terms
 // follow in the reference's order (flat wall, then sites m ascending).
+// ---- FAST-path building blocks of the sweep kernel ---------------------------
+#ifndef SMCB_RINT_MODE
+#define SMCB_RINT_MODE 0
+#endif
+// round-to-nearest-even of a small number: FRND.F64 (XU pipe) or the 2^52+2^51
+// add/subtract trick (two DADDs on the FP64 pipe); both are exact.
+__device__ __forceinline__ double rint_xu(double s) { return rint(s); }
+__device__ __forceinline__ double rint_magic(double s)
+{
+    return __dsub_rn(__dadd_rn(s, 6755399441055744.0), 6755399441055744.0);
+}
+__device__ __forceinline__ double wrap_unit_x(double s)
+{
+#if SMCB_RINT_MODE == 1
+    return s - rint_magic(s);
+#else
+    return s - rint_xu(s);
+#endif
+}
+__device__ __forceinline__ double wrap_unit_y(double s)
+{
+#if SMCB_RINT_MODE == 0
+    return s - rint_xu(s);
+#else
+    return s - rint_magic(s);
+#endif
+}
+
+// 1/x for a positive normal x to ~1 ulp without the slow-path call of the IEEE
+// division: MUFU.RCP64H seed (rcp.approx.ftz.f64, 2^-23) + two Newton steps.
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// Sum four per-lane values over the warp with a transposed butterfly: the first two
+// exchange steps halve the number of live values instead of reducing each of the four
+// separately (20 SHFL + 6 DADD instead of 40 + 20).  Every lane returns all four totals.
+__device__ __forceinline__ void warp_sum4(int lane, double &a, double &b, double &c, double &d)
+{
+    const bool hi = (lane & 16) != 0;
+    double k0 = hi ? c : a, k1 = hi ? d : b;          // kept pair
+    const double s0 = hi ? a : c, s1 = hi ? b : d;    // sent pair
+    k0 += __shfl_xor_sync(FULL, s0, 16);
+    k1 += __shfl_xor_sync(FULL, s1, 16);
+    const bool mid = (lane & 8) != 0;
+    double v = mid ? k1 : k0;
+    const double w = mid ? k0 : k1;
+    v += __shfl_xor_sync(FULL, w, 8);
+    v += __shfl_xor_sync(FULL, v, 4);
+    v += __shfl_xor_sync(FULL, v, 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    a = __shfl_sync(FULL, v, 0);
+    b = __shfl_sync(FULL, v, 8);
+    c = __shfl_sync(FULL, v, 16);
+    d = __shfl_sync(FULL, v, 24);
+}
+
+// per-lane surface site (lane m < M*M owns site m = i*M + j at (i*dw, j*dw), SMC.c:745-750)
+struct LaneSite {
+    double sx, sy, ca, cb;
+    bool on;
+};
+
+// FAST pass of the sweep kernel.  xs/ys/zs hold the lane's particles in units of L
+// (x/L, y/L, z/L): the minimum image is then s - rint(s) and the squared distance in
+// box units is compared with rc2/L^2, 9 FP64-pipe instructions per pair.  Phase 1 walks
+// all K slots and only records which are inside the cutoff; phase 2 (rare in the gas)
+// re-reads each hit's unscaled position from the shared-memory mirror and adds its 12-6
+// terms exactly as k_evaluate's FAST path does.  okmask: bit k set when slot k is a real particle
+// other than the trial particle.
+template <int K>
+__device__ __forceinline__ void sweep_pass_fast(const Box &b, const LaneSite &site, const double *__restrict__ W,
+                                                int lane, unsigned okmask, double px, double py, double pz,
+                                                const double (&xs)[K], const double (&ys)[K], const double (&zs)[K],
+                                                const double *smx, const double *smy, const double *smz,
+                                                double rc2s, double zperiod_s, double inv_zperiod_s,
+                                                double &U, double &Fx, double &Fy, double &Fz, unsigned long long &cnt)
+{
+    const double psx = px * b.invL, psy = py * b.invL, psz = pz * b.invL;
+    unsigned hits = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double sx = wrap_unit_x(psx - xs[k]);
+        const double sy = wrap_unit_y(psy - ys[k]);
+        double sz = psz - zs[k];
+        if (b.pz) sz = fma(-zperiod_s, rint(sz * inv_zperiod_s), sz);
+        const double r2s = fma(sz, sz, fma(sy, sy, sx * sx));
+        if (r2s < rc2s) hits |= 1u << k;
+    }
+    hits &= okmask;
+    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+    while (hits) {                                     // divergent, rare in the gas phase
+        const int k = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int j = lane + 32 * k;                    // unscaled neighbour from the shared-memory mirror
+        double dx, dy, dz;
+        const double r2 = pair_sep<false>(b, px, py, pz, smx[j], smy[j], smz[j], dx, dy, dz);
+        if (r2 < b.rc2) {
+            const double i2 = fast_rcp(r2);
+            const double i6 = i2 * i2 * i2;
+            e += fma(i6, i6, -i6);
+            const double g = i2 * i6 * fma(48.0, i6, -24.0);
+            fx = fma(g, dx, fx);
+            fy = fma(g, dy, fy);
+            fz = fma(g, dz, fz);
+            cnt++;
+        }
+    }
+    double dzw = 0.0;
+    if (b.wall) {
+        dzw = wall_dz<false>(b, pz);
+        if (dzw * dzw < b.rc2) {                       // warp-uniform: no site can be in range otherwise
+            if (site.on) {
+                const double dx = min_image<false>(px - site.sx, b.L, b.invL);
+                const double dy = min_image<false>(py - site.sy, b.L, b.invL);
+                const double r2 = fma(dzw, dzw, fma(dy, dy, dx * dx));
+                if (r2 < b.rc2) {
+                    const double i2 = fast_rcp(r2);
+                    const double i6 = i2 * i2 * i2;
+                    const double a6 = site.ca * i6;
+                    e += fma(a6, i6, -site.cb * i6);
+                    const double g = i2 * i6 * fma(48.0, a6, -24.0 * site.cb);
+                    fx = fma(g, dx, fx);
+                    fy = fma(g, dy, fy);
+                    fz = fma(g, dzw, fz);
+                }
+            }
+            const int MM = b.M * b.M;
+            const double dw = b.L / b.M;
+            for (int m = lane + 32; m < MM; m += 32) {   // M > 5 only
+                const int i = m / b.M, j = m - i * b.M;
+                const double dx = min_image<false>(px - i * dw, b.L, b.invL);
+                const double dy = min_image<false>(py - j * dw, b.L, b.invL);
+                const double r2 = fma(dzw, dzw, fma(dy, dy, dx * dx));
+                if (r2 < b.rc2) {
+                    double et, g;
+                    lj_terms<false, false>(r2, W[2 * m], W[2 * m + 1], et, g);
+                    e += et;
+                    fx = fma(g, dx, fx);
+                    fy = fma(g, dy, fy);
+                    fz = fma(g, dzw, fz);
+                }
+            }
+        }
+    }
+    warp_sum4(lane, e, fx, fy, fz);
+    if (b.wall) {                                       // flat wall: same on every lane, no cutoff
+        const double i2 = fast_rcp(dzw * dzw);
+        const double i6 = i2 * i2 * i2;
+        const double a6 = b.a0 * i6;
+        e += fma(a6, i6, -b.b0 * i6);
+        fz = fma(i2 * i6 * fma(48.0, a6, -24.0 * b.b0), dzw, fz);
+    }
+    U = 4.0 * e;
+    Fx = fx; Fy = fy; Fz = fz;
+}
+
 template <int K, bool STRICT>
 __device__ __forceinline__ void sweep_pass(const Box &b, const double *__restrict__ W, int N, int lane,
                                            int owner, int slot, double px, double py, double pz,
@@ -265,7 +429,7 @@ __device__ __forceinline__ void sweep_pass(const Box &b, const double *__restric
 }
 
 template <int K, bool STRICT, bool FED>
-__global__ void __launch_bounds__(32) k_sweep(DevChains d, SweepArgs a)
+__global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, SweepArgs a)
 {
     const int lane = threadIdx.x, chain = blockIdx.x;
     const int N = d.N, Npad = d.Npad;
@@ -276,17 +440,31 @@ __global__ void __launch_bounds__(32) k_sweep(DevChains d, SweepArgs a)
     const double *W = d.W + (size_t)cp.wall * 2 * d.M * d.M;
     double *P = d.pos + (size_t)chain * 3 * Npad;
 
+    // registers: the lane's particles, unscaled (STRICT) or in units of L (FAST)
     double x[K], y[K], z[K];
+    unsigned validmask = 0;
+    const double rscale = STRICT ? 1.0 : b.invL;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int j = lane + 32 * k;
         const bool in = j < N;
-        x[k] = in ? P[j] : 0.0;
-        y[k] = in ? P[Npad + j] : 0.0;
-        z[k] = in ? P[2 * Npad + j] : 0.0;
-        if (j < Npad) { sx[j] = x[k]; sy[j] = y[k]; sz[j] = z[k]; }
+        const double X = in ? P[j] : 0.0, Y = in ? P[Npad + j] : 0.0, Z = in ? P[2 * Npad + j] : 0.0;
+        if (j < Npad) { sx[j] = X; sy[j] = Y; sz[j] = Z; }
+        x[k] = X * rscale; y[k] = Y * rscale; z[k] = Z * rscale;
+        if (in) validmask |= 1u << k;
     }
     __syncwarp();
+    LaneSite site;
+    site.on = b.wall && lane < d.M * d.M;
+    {
+        const int si = lane / d.M, sj = lane - si * d.M;
+        const double dw = b.L / d.M;
+        site.sx = si * dw; site.sy = sj * dw;
+        site.ca = site.on ? W[2 * lane] : 0.0;
+        site.cb = site.on ? W[2 * lane + 1] : 0.0;
+    }
+    const double rc2s = b.rc2 * b.invL * b.invL * (1.0 + 1e-12);   // phase-1 screen, exact test in phase 2
+    const double zperiod_s = b.Lz * b.invL, inv_zperiod_s = b.L * b.invLz;
 
     const double AoT = b.A / b.T;
     const double sigma = sqrt(2.0 * b.A);            // vecBoxMuller(sqrt(2.0*A), ...)  SMC.c:284
@@ -334,8 +512,10 @@ __global__ void __launch_bounds__(32) k_sweep(DevChains d, SweepArgs a)
                 const int owner = n & 31, slot = n >> 5;
                 const double px = sx[n], py = sy[n], pz = sz[n];
 
+                const unsigned okmask = validmask & ~((lane == owner) ? (1u << slot) : 0u);
                 double Um, Fmx, Fmy, Fmz;              // SMC.c:300-304
-                sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, px, py, pz, x, y, z, Um, Fmx, Fmy, Fmz, cnt);
+                if (STRICT) sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, px, py, pz, x, y, z, Um, Fmx, Fmy, Fmz, cnt);
+                else sweep_pass_fast<K>(b, site, W, lane, okmask, px, py, pz, x, y, z, sx, sy, sz, rc2s, zperiod_s, inv_zperiod_s, Um, Fmx, Fmy, Fmz, cnt);
 
                 double dX, dY, dZ;                      // SMC.c:307-309
                 if (STRICT) {
@@ -353,7 +533,8 @@ __global__ void __launch_bounds__(32) k_sweep(DevChains d, SweepArgs a)
                 if (b.pz) qz = min_image<STRICT>(qz, b.Lz, b.invLz);
 
                 double Un, Fnx, Fny, Fnz;              // SMC.c:319-321
-                sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, qx, qy, qz, x, y, z, Un, Fnx, Fny, Fnz, cnt);
+                if (STRICT) sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, qx, qy, qz, x, y, z, Un, Fnx, Fny, Fnz, cnt);
+                else sweep_pass_fast<K>(b, site, W, lane, okmask, qx, qy, qz, x, y, z, sx, sy, sz, rc2s, zperiod_s, inv_zperiod_s, Un, Fnx, Fny, Fnz, cnt);
 
                 double ap;                              // SMC.c:326-329
                 if (STRICT) {
@@ -371,7 +552,7 @@ __global__ void __launch_bounds__(32) k_sweep(DevChains d, SweepArgs a)
                         sx[n] = qx; sy[n] = qy; sz[n] = qz;
 #pragma unroll
                         for (int k = 0; k < K; k++)
-                            if (k == slot) { x[k] = qx; y[k] = qy; z[k] = qz; }
+                            if (k == slot) { x[k] = qx * rscale; y[k] = qy * rscale; z[k] = qz * rscale; }
                     }
                     E += Un - Um;                       // SMC.c:341
                     nacc++;
@@ -382,10 +563,8 @@ __global__ void __launch_bounds__(32) k_sweep(DevChains d, SweepArgs a)
         }
     }
 
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const int j = lane + 32 * k;
-        if (j < N) { P[j] = x[k]; P[Npad + j] = y[k]; P[2 * Npad + j] = z[k]; }
+    for (int j = lane; j < N; j += 32) {               // the shared-memory mirror holds the exact positions
+        P[j] = sx[j]; P[Npad + j] = sy[j]; P[2 * Npad + j] = sz[j];
     }
     unsigned long long tot = cnt;
 #pragma unroll
@@ -400,6 +579,10 @@ __global__ void __launch_bounds__(32) k_sweep(DevChains d, SweepArgs a)
         }
     }
 }
+
+}  // namespace smcb
+#include "sweep_cached.cuh"
+namespace smcb {
 
 // ========================================================== k_allparticle ===
 // One CTA per chain, persistent over nsteps.  Shared memory holds the current

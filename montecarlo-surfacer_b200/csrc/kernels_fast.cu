@@ -2,6 +2,7 @@
 // that have no strict/fast distinction (gather, layout transposes, DFMA peak).
 #define SMCB_MISC_KERNELS
 #include "launch.h"
+#define SMCB_TU_IS_STRICT 0
 #define SMCB_TU_STRICT false
 #define SMCB_TU_SUFFIX fast
 #include "launchers.inl"

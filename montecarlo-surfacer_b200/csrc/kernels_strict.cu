@@ -7,6 +7,7 @@
 #error "kernels_strict.cu must be built with --fmad=false -DSMCB_FMAD_OFF"
 #endif
 #include "launch.h"
+#define SMCB_TU_IS_STRICT 1
 #define SMCB_TU_STRICT true
 #define SMCB_TU_SUFFIX strict
 #include "launchers.inl"

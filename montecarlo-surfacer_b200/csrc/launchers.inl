@@ -24,9 +24,24 @@ cudaError_t SMCB_CAT(launch_evaluate_, SMCB_TU_SUFFIX)(const DevChains &d, const
 template <int K>
 static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
 {
+#if SMCB_TU_IS_STRICT
     const size_t smem = (size_t)3 * d.Npad * sizeof(double);
-    if (fed) k_sweep<K, SMCB_TU_STRICT, true><<<d.C, 32, smem, st>>>(d, a);
-    else     k_sweep<K, SMCB_TU_STRICT, false><<<d.C, 32, smem, st>>>(d, a);
+    if (fed) k_sweep<K, true, true><<<d.C, 32, smem, st>>>(d, a);
+    else     k_sweep<K, true, false><<<d.C, 32, smem, st>>>(d, a);
+#else
+    const int MMpad = (d.M * d.M + 3) & ~3;
+    const size_t smem = ChainSmem::bytes(d.Npad, MMpad);
+    cudaError_t err;
+    if (fed) {
+        auto kern = k_sweep_cached<K, true>;
+        if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        kern<<<d.C, 32, smem, st>>>(d, a);
+    } else {
+        auto kern = k_sweep_cached<K, false>;
+        if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        kern<<<d.C, 32, smem, st>>>(d, a);
+    }
+#endif
     return cudaGetLastError();
 }
 

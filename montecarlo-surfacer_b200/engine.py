@@ -44,7 +44,8 @@ def default_params(L=33.0, Lz=240.0, T=1.1, A=None, rc2=9.0, a0=A0_DEFAULT, b0=B
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsmcb200.so")
+    """in-tree libsmcb200.so; SMCB200_LIB selects another build of the SAME library (kernel experiments)"""
+    return os.environ.get("SMCB200_LIB") or os.path.join(_HERE, "libsmcb200.so")
 
 
 _lib = None
@@ -92,6 +93,8 @@ def load_library():
         "smcb_last_pair_counts": [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
         "smcb_measure_fp64_peak": [P, dp, C.POINTER(C.c_float)],
         "smcb_device_positions": [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)],
+        "smcb_debug_capture_cache": [P, C.c_int],
+        "smcb_debug_get_cache": [P, P, P, P],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -313,6 +316,17 @@ class Engine:
         t, ms = C.c_double(), C.c_float()
         self._ck(self.lib.smcb_measure_fp64_peak(self._h, C.byref(t), C.byref(ms)))
         return t.value, ms.value
+
+    def debug_capture_cache(self, on=True):
+        self._ck(self.lib.smcb_debug_capture_cache(self._h, int(on)))
+
+    def debug_get_cache(self):
+        """(e_tot [C,N], f_tot [C,3N], nb [C,N]) held by the FAST sweep kernel at its end"""
+        e = np.empty((self.C, self.N))
+        f = np.empty((self.C, 3 * self.N))
+        nb = np.empty((self.C, self.N))
+        self._ck(self.lib.smcb_debug_get_cache(self._h, _ptr(e), _ptr(f), _ptr(nb)))
+        return e, f, nb
 
     def stream(self):
         return self.lib.smcb_stream(self._h)

@@ -148,3 +148,84 @@ def test_thermalisation_scale_and_bulk_mode(orc):
     np.testing.assert_array_equal(R, Ro)
     assert E == Eo
     assert np.all(np.abs(R) <= L / 2 + 1e-12)
+
+
+@pytest.mark.parametrize("N,A,T,nsweeps,kind", [(256, 0.01, 0.9, 30, "droplet"), (108, 1.1, 1.1, 60, "mixed"),
+                                                (100, 0.02, 0.8, 40, "droplet"), (500, 0.02, 1.0, 6, "droplet")])
+def test_fast_sweep_cache_stays_consistent(orc, N, A, T, nsweeps, kind):
+    """The FAST sweep kernel keeps per-particle energy/force/neighbour caches and corrects them
+    incrementally (csrc/sweep_cached.cuh).  After many sweeps in one launch - dense droplets with
+    ~80 partners per particle included - the caches must equal a fresh evaluation of the final
+    configuration, the neighbour counts exactly, and the running energy the recomputed one."""
+    M = 3 if N != 100 else 2
+    L, Lz = geom(N)
+    s = make_sys(N, M, L, Lz)
+    rng = np.random.default_rng(N + nsweeps)
+    W = GOLDEN_W_M3.copy() if M == 3 else random_walls(M, rng)
+    nchains = 6
+    if kind == "droplet":
+        R0 = np.stack([config_droplet(N, L, Lz, rng, jitter=0.03, nz=4 if N <= 256 else 8) for _ in range(nchains)])
+    else:
+        R0 = mixed_configs(N, L, Lz, nchains, seed=N, orc=orc)
+    with smcb.Engine(nchains, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
+        eng.set_positions(R0)
+        eng.set_rng(7, 0, 0)
+        eng.debug_capture_cache(True)
+        eng.sweep(nsweeps, smcb.FAST)
+        ce, cf, nb = eng.debug_get_cache()
+        E, na, nt = eng.chain_state()
+        R = eng.get_positions()
+        ev = eng.evaluate(smcb.FAST)
+    assert na.sum() > 0.05 * nt.sum(), "too few accepted moves to exercise the cache updates"
+    assert not np.array_equal(R, R0)
+    e_tot = ev["e_lj"] + ev["e_wall"]
+    f_tot = ev["f_lj"] + ev["f_wall"]
+    for c in range(nchains):
+        # exact neighbour counts from the oracle geometry
+        X = R[c].reshape(N, 3)
+        d = X[:, None, :] - X[None, :, :]
+        d[:, :, 0] -= L * np.rint(d[:, :, 0] / L)
+        d[:, :, 1] -= L * np.rint(d[:, :, 1] / L)
+        r2 = np.einsum("ijk,ijk->ij", d, d)
+        np.fill_diagonal(r2, 1e30)
+        margin = np.abs(r2 - 9.0) < 1e-9
+        nbo = (r2 < 9.0).sum(axis=1)
+        if not margin.any():
+            np.testing.assert_array_equal(nb[c], nbo)
+        assert rel_err(ce[c], e_tot[c], floor=max(1.0, np.abs(e_tot[c]).max() * 1e-3)) < 1e-11
+        assert rel_err(cf[c], f_tot[c], floor=max(1.0, np.abs(f_tot[c]).max() * 1e-3)) < 1e-11
+        Erec = ev["U_lj"][c] + ev["U_wall"][c]
+        assert abs(E[c] - Erec) <= 1e-10 * max(1.0, abs(Erec))
+        # and against the oracle for one chain's per-particle forces
+        if c == 0:
+            fo = np.concatenate([orc.force_single(s, R[c], i) + orc.walls_force(s, R[c][3 * i:3 * i + 3], W) for i in range(N)])
+            assert rel_err(cf[c], fo, floor=max(1.0, np.abs(fo).max() * 1e-3)) < 1e-11
+
+
+def test_fast_sweep_multi_sweep_launch_tracks_oracle(orc):
+    """several sweeps inside ONE launch (caches carried from trial to trial and sweep to sweep)
+    against the oracle on the same fed numbers; chaos amplifies 1e-16 by about a decade per 10
+    sweeps, so 8 sweeps must still agree to 1e-9 and take identical accept decisions"""
+    N, M, T, A = 108, 3, 1.1, 1.1
+    L, Lz = geom(N)
+    s = make_sys(N, M, L, Lz)
+    W = GOLDEN_W_M3.copy()
+    nchains, nsweeps = 4, 8
+    rng = np.random.default_rng(31)
+    R0 = mixed_configs(N, L, Lz, nchains, seed=77, orc=orc)
+    streams = np.stack([make_stream(N, nsweeps, rng) for _ in range(nchains)], axis=1)
+    displ, off, u = expand_streams(orc, N, A, streams)
+    with smcb.Engine(nchains, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
+        eng.set_positions(R0)
+        eng.refresh_energy(smcb.FAST)
+        E0 = eng.chain_state()[0]
+        acc = eng.sweep_fed(displ, off, u, mode=smcb.FAST, want_accepted=True)
+        R = eng.get_positions()
+        E = eng.chain_state()[0]
+    for c in range(nchains):
+        Ro, Eo, tot, flags = _oracle_run(orc, s, R0[c], W, A, T, displ[:, c], off[:, c], u[:, c], E0[c])
+        np.testing.assert_array_equal(acc[:, c], flags)
+        assert rel_err(R[c], Ro) < 1e-9
+        assert abs(E[c] - Eo) <= 1e-9 * max(1.0, abs(Eo))
