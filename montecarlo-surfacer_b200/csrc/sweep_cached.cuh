@@ -186,8 +186,11 @@ __device__ __forceinline__ void eval_point(const Box &b, const ScreenConsts &sc,
     U = 4.0 * e; Fx = fx; Fy = fy; Fz = fz;
 }
 
+#ifndef SMCB_SWEEP_MINB
+#define SMCB_SWEEP_MINB 14
+#endif
 template <int K, bool FED>
-__global__ void __launch_bounds__(32, (K <= 8 ? 14 : 8)) k_sweep_cached(DevChains d, SweepArgs a)
+__global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_cached(DevChains d, SweepArgs a)
 {
     const int lane = threadIdx.x, chain = blockIdx.x;
     const int N = d.N, Npad = d.Npad;
@@ -240,8 +243,26 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 14 : 8)) k_sweep_cached(DevChain
     const double quarterAoT = 0.25 * AoT, invT = 1.0 / b.T;
     double E = d.E[chain];
     int nacc = 0;
-    unsigned long long cnt = 0;
+    unsigned cnt = 0;                                // per-lane, < 2^32 per launch
     const RngId id{a.rng.k0, a.rng.k1, a.rng.chain0 + (uint32_t)chain};
+
+    // Physical register slot 0 always holds the slot that is being visited: the visiting
+    // order n = (nn+offset)%N walks the slots cyclically, so the register arrays are rotated
+    // by one at every slot boundary (48 moves per 32 trials) instead of being updated through
+    // a run-time index at every accepted trial.  `rot` = logical slot held at physical 0.
+    int rot = 0;
+    auto rotate = [&]() {
+        if (K > 1) {
+            const double tx = xs[0], ty = ys[0], tz = zs[0];
+#pragma unroll
+            for (int k = 0; k + 1 < K; k++) { xs[k] = xs[k + 1]; ys[k] = ys[k + 1]; zs[k] = zs[k + 1]; }
+            xs[K - 1] = tx; ys[K - 1] = ty; zs[K - 1] = tz;
+            validmask = (validmask >> 1) | ((validmask & 1u) << (K - 1));
+            rot = (rot + 1 == K) ? 0 : rot + 1;
+        }
+    };
+    // physical slot k holds logical slot (k + rot) mod K
+    auto particle_of = [&](int k) { int sl = k + rot; if (sl >= K) sl -= K; return lane + 32 * sl; };
 
     for (int sw = 0; sw < a.nsweeps; sw++) {
         const unsigned long long step = a.rng.step0 + (unsigned long long)sw;
@@ -254,109 +275,147 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 14 : 8)) k_sweep_cached(DevChain
             rng_step_scalars(id, step, o, unused);
             offset = o;
         }
-        const int off = (int)(offset % N);
-        for (int nn0 = 0; nn0 < N; nn0 += 32) {
-            // each lane prepares the random inputs of one of the next 32 trials
-            const int nnl = nn0 + lane;
-            int nl = nnl + off;                        // n = (nn+offset)%N  SMC.c:294
-            if (nl >= N) nl -= N;
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0, ul = 2.0;
-            if (nnl < N) {
-                if (FED) {
-                    const double *dsp = a.displ + sci * 3 * N;
-                    g0 = dsp[3 * nl]; g1 = dsp[3 * nl + 1]; g2 = dsp[3 * nl + 2];
-                    ul = a.u[sci * N + nnl];
-                } else {
-                    rng_particle_gauss(id, step, (uint32_t)nl, g0, g1, g2);
-                    g0 *= sigma; g1 *= sigma; g2 *= sigma;
-                    ul = rng_particle_uniform(id, step, (uint32_t)nl);
+        const int off = (int)(offset % N);             // first particle of the sweep: n = (nn+offset)%N, SMC.c:294
+        const int slot0 = off >> 5, t0 = off & 31;
+        while (rot != slot0) rotate();
+        // K+1 segments: [off .. end of its slot], the following slots cyclically, then [start of slot0 .. off-1]
+        for (int seg = 0; seg <= K; seg++) {
+            const int slot = rot;
+            const int tb = (seg == 0) ? t0 : 0;
+            int te = min(32, N - 32 * slot);            // particles of this slot that exist
+            if (seg == K) te = min(te, t0);
+            if (tb < te) {
+                // each lane prepares the random inputs of its own particle of this slot
+                const int nl = 32 * slot + lane;
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, lul = 0.0;
+                if (lane >= tb && lane < te) {
+                    double ul;
+                    if (FED) {
+                        const double *dsp = a.displ + sci * 3 * N;
+                        g0 = dsp[3 * nl]; g1 = dsp[3 * nl + 1]; g2 = dsp[3 * nl + 2];
+                        int nn = nl - off;              // trial index in visiting order (u is per trial, SMC.c:335)
+                        if (nn < 0) nn += N;
+                        ul = a.u[sci * N + nn];
+                    } else {
+                        rng_particle_gauss(id, step, (uint32_t)nl, g0, g1, g2);
+                        g0 *= sigma; g1 *= sigma; g2 *= sigma;
+                        ul = rng_particle_uniform(id, step, (uint32_t)nl);
+                    }
+                    lul = log(ul);                      // u < exp(x)  <=>  log(u) < x, evaluated lane-parallel
                 }
-            }
-            const int tmax = min(32, N - nn0);
-            for (int t = 0; t < tmax; t++) {
-                const int n = __shfl_sync(FULL, nl, t);
-                const double gx = __shfl_sync(FULL, g0, t);
-                const double gy = __shfl_sync(FULL, g1, t);
-                const double gz = __shfl_sync(FULL, g2, t);
-                const double uu = __shfl_sync(FULL, ul, t);
-                const int owner = n & 31, slot = n >> 5;
-                const unsigned okmask = validmask & ~((lane == owner) ? (1u << slot) : 0u);
-                const double px = s.x[n], py = s.y[n], pz = s.z[n];
-                const double Um = s.ce[n], Fmx = s.cfx[n], Fmy = s.cfy[n], Fmz = s.cfz[n];   // SMC.c:300-304, cached
-                const int nbm = s.nb[n];
+                for (int t = tb; t < te; t++) {
+                    const int n = 32 * slot + t;
+                    const unsigned okmask = validmask & ~((lane == t) ? 1u : 0u);
+                    const int nbm = s.nb[n];
+                    double dX, dY, dZ, qx, qy, qz;
+                    {
+                        // proposal from the cached force of particle n (SMC.c:303-316)
+                        dX = fma(s.cfx[n], AoT, __shfl_sync(FULL, g0, t));
+                        dY = fma(s.cfy[n], AoT, __shfl_sync(FULL, g1, t));
+                        dZ = fma(s.cfz[n], AoT, __shfl_sync(FULL, g2, t));
+                        qx = min_image<false>(s.x[n] + dX, b.L, b.invL);
+                        qy = min_image<false>(s.y[n] + dY, b.L, b.invL);
+                        qz = s.z[n] + dZ;
+                        if (b.pz) qz = min_image<false>(qz, b.Lz, b.invLz);
+                    }
+                    const double qsx = qx * b.invL, qsy = qy * b.invL, qsz = qz * b.invL;
 
-                const double dX = fma(Fmx, AoT, gx), dY = fma(Fmy, AoT, gy), dZ = fma(Fmz, AoT, gz);   // SMC.c:307-309
-                double qx = min_image<false>(px + dX, b.L, b.invL);                                  // SMC.c:311-316
-                double qy = min_image<false>(py + dY, b.L, b.invL);
-                double qz = pz + dZ;
-                if (b.pz) qz = min_image<false>(qz, b.Lz, b.invLz);
+                    // flat wall at the proposal: uniform, no cutoff; started early, off the pair loop's path
+                    double ew = 0.0, fzw = 0.0, dzw = 0.0;
+                    bool near = false;
+                    if (b.wall) {
+                        dzw = wall_dz<false>(b, qz);
+                        near = dzw * dzw < b.rc2;
+                        add_zwall(b, dzw, ew, fzw);
+                    }
 
-                // one pass: the proposed position (always) and the old one (only if it has partners)
-                unsigned hits_new, hits_old = 0;
-                if (nbm) {
-                    screen_slots2<K>(b, sc, qx * b.invL, qy * b.invL, qz * b.invL, px * b.invL, py * b.invL, pz * b.invL,
-                                     xs, ys, zs, hits_new, hits_old);
-                    hits_old &= okmask;
-                } else {
-                    hits_new = screen_slots<K>(b, sc, qx * b.invL, qy * b.invL, qz * b.invL, xs, ys, zs);
-                }
-                hits_new &= okmask;
-                double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-                const unsigned in_new = add_hits(b, s, lane, hits_new, qx, qy, qz, e, fx, fy, fz);
-                double dzw = 0.0;
-                if (b.wall) {
-                    dzw = wall_dz<false>(b, qz);
-                    if (dzw * dzw < b.rc2) add_sites(b, s, lane, MMpad, qx, qy, dzw, e, fx, fy, fz);
-                }
-                warp_sum4(lane, e, fx, fy, fz);
-                if (b.wall) add_zwall(b, dzw, e, fz);
-                const double Un = 4.0 * e, Fnx = fx, Fny = fy, Fnz = fz;                              // SMC.c:319-321
+                    // one pass: the proposed position (always) and the old one (only if it has partners)
+                    unsigned hits_new, hits_old = 0;
+                    if (nbm) {
+                        screen_slots2<K>(b, sc, qsx, qsy, qsz, s.x[n] * b.invL, s.y[n] * b.invL, s.z[n] * b.invL,
+                                         xs, ys, zs, hits_new, hits_old);
+                        hits_old &= okmask;
+                    } else {
+                        hits_new = screen_slots<K>(b, sc, qsx, qsy, qsz, xs, ys, zs);
+                    }
+                    hits_new &= okmask;
 
-                // SMC.c:326-329: ap = exp(-(Un-Um + d.(Fn+Fm)/2 + (Fn^2-Fm^2) A/(4T))/T)
-                const double f2 = fma(Fnx, Fnx, fma(Fny, Fny, Fnz * Fnz)) - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
-                const double dr = fma(dX, Fnx + Fmx, fma(dY, Fny + Fmy, dZ * (Fnz + Fmz)));
-                const double ap = exp(-((Un - Um) + 0.5 * dr + f2 * quarterAoT) * invT);
-                const bool acc = uu < ap;               // SMC.c:335
-                cnt += __popc(in_new) + (lane == 0 ? nbm : 0);   // partners at the new + at the old position
-                if (acc) {
-                    // partners lose the old pair terms and gain the new ones (force on j from n = -g d)
-                    unsigned ho = hits_old;
-                    while (ho) {
-                        const int k = __ffs(ho) - 1;
-                        ho &= ho - 1;
-                        const int j = lane + 32 * k;
-                        double et, hx, hy, hz;
-                        if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
-                            s.ce[j] -= 4.0 * et; s.cfx[j] += hx; s.cfy[j] += hy; s.cfz[j] += hz;
-                            s.nb[j] -= 1;
+                    // gas-phase fast path: nobody in range of the proposal -> all pair and site sums are exactly 0
+                    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+                    unsigned in_new = 0;
+                    const bool work = __any_sync(FULL, hits_new != 0) || near;
+                    if (work) {
+                        while (hits_new) {
+                            const int k = __ffs(hits_new) - 1;
+                            hits_new &= hits_new - 1;
+                            const int j = particle_of(k);
+                            double et, hx, hy, hz;
+                            if (pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
+                                e += et; fx += hx; fy += hy; fz += hz;
+                                in_new |= 1u << k;
+                            }
                         }
+                        if (near) add_sites(b, s, lane, MMpad, qx, qy, dzw, e, fx, fy, fz);
+                        warp_sum4(lane, e, fx, fy, fz);
                     }
-                    unsigned hn = in_new;
-                    while (hn) {
-                        const int k = __ffs(hn) - 1;
-                        hn &= hn - 1;
-                        const int j = lane + 32 * k;
-                        double et, hx, hy, hz;
-                        pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz);
-                        s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
-                        s.nb[j] += 1;
+                    const double Un = 4.0 * (e + ew), Fnx = fx, Fny = fy, Fnz = fz + fzw;                 // SMC.c:319-321
+
+                    // SMC.c:326-335: accept iff u < exp(-(Un-Um + d.(Fn+Fm)/2 + (Fn^2-Fm^2) A/(4T))/T)
+                    const double Um = s.ce[n], Fmx = s.cfx[n], Fmy = s.cfy[n], Fmz = s.cfz[n];           // SMC.c:300-304, cached
+                    const double f2 = fma(Fnx, Fnx, fma(Fny, Fny, Fnz * Fnz)) - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
+                    const double dr = fma(dX, Fnx + Fmx, fma(dY, Fny + Fmy, dZ * (Fnz + Fmz)));
+                    const double xarg = -((Un - Um) + 0.5 * dr + f2 * quarterAoT) * invT;
+                    const double lu = __shfl_sync(FULL, lul, t);
+                    const bool acc = (lu < xarg) && (xarg > -745.1332191019411);    // exp underflows to 0 below that
+                    cnt += __popc(in_new) + (lane == 0 ? nbm : 0);   // partners at the new + at the old position
+                    if (acc) {
+                        // partners lose the old pair terms and gain the new ones (force on j from n = -g d)
+                        if (nbm) {
+                            const double px = s.x[n], py = s.y[n], pz = s.z[n];
+                            while (hits_old) {
+                                const int k = __ffs(hits_old) - 1;
+                                hits_old &= hits_old - 1;
+                                const int j = particle_of(k);
+                                double et, hx, hy, hz;
+                                if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
+                                    s.ce[j] -= 4.0 * et; s.cfx[j] += hx; s.cfy[j] += hy; s.cfz[j] += hz;
+                                    s.nb[j] -= 1;
+                                }
+                            }
+                        }
+                        int nbn = 0;
+                        if (work) {
+                            unsigned hn = in_new;
+                            while (hn) {
+                                const int k = __ffs(hn) - 1;
+                                hn &= hn - 1;
+                                const int j = particle_of(k);
+                                double et, hx, hy, hz;
+                                pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz);
+                                s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
+                                s.nb[j] += 1;
+                            }
+                            nbn = __reduce_add_sync(FULL, __popc(in_new));
+                        }
+                        __syncwarp();                    // partner updates read the old position of n: order before overwriting it
+                        if (lane == t) {                 // the owner: physical slot 0 is the visited slot
+                            s.x[n] = qx; s.y[n] = qy; s.z[n] = qz;
+                            s.ce[n] = Un; s.cfx[n] = Fnx; s.cfy[n] = Fny; s.cfz[n] = Fnz;
+                            s.nb[n] = (unsigned short)nbn;
+                            xs[0] = qsx; ys[0] = qsy; zs[0] = qsz;
+                        }
+                        E += Un - Um;                   // SMC.c:341
+                        nacc++;
                     }
-                    const int nbn = __reduce_add_sync(FULL, __popc(in_new));
-                    if (lane == owner) {
-                        s.x[n] = qx; s.y[n] = qy; s.z[n] = qz;
-                        s.ce[n] = Un; s.cfx[n] = Fnx; s.cfy[n] = Fny; s.cfz[n] = Fnz;
-                        s.nb[n] = (unsigned short)nbn;
-                        const double qsx = qx * b.invL, qsy = qy * b.invL, qsz = qz * b.invL;
-#pragma unroll
-                        for (int k = 0; k < K; k++)
-                            if (k == slot) { xs[k] = qsx; ys[k] = qsy; zs[k] = qsz; }
+                    if (FED && a.accepted != nullptr && lane == 0) {
+                        int nn = n - off;
+                        if (nn < 0) nn += N;
+                        a.accepted[sci * N + nn] = acc ? 1 : 0;
                     }
-                    E += Un - Um;                       // SMC.c:341
-                    nacc++;
+                    __syncwarp();
                 }
-                if (FED && a.accepted != nullptr && lane == 0) a.accepted[sci * N + nn0 + t] = acc ? 1 : 0;
-                __syncwarp();
             }
+            if (seg < K) rotate();
         }
     }
 

@@ -4,7 +4,7 @@
 # `--set full` capture of the named kernel (B200_PROFILING.md recipe).  Outputs in gpurun_out/.
 set -uo pipefail
 TAG="${1:-r01}"; KRE="${2:-k_sweep}"; shift 2 || true
-CMD="python bench.py --steps 1 --warmup 3 --sweeps-per-step 4 --no-e2e --no-cpu-baseline $*"
+CMD="python bench.py --steps 1 --warmup 3 --sweeps-per-step ${SPS:-40} --chains ${CHAINS:-2072} --no-e2e --no-cpu-baseline $*"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
