@@ -55,7 +55,7 @@ struct ScreenConsts {
 
 // phase 1: which of the lane's K slots are within the (slightly inflated) cutoff of the
 // point (psx,psy,psz) given in box units
-template <int K>
+template <int K, bool PZ>
 __device__ __forceinline__ unsigned screen_slots(const Box &b, const ScreenConsts &sc, double psx, double psy, double psz,
                                                  const double (&xs)[K], const double (&ys)[K], const double (&zs)[K])
 {
@@ -65,7 +65,7 @@ __device__ __forceinline__ unsigned screen_slots(const Box &b, const ScreenConst
         const double sx = wrap_unit_x(psx - xs[k]);
         const double sy = wrap_unit_y(psy - ys[k]);
         double sz = psz - zs[k];
-        if (b.pz) sz = fma(-sc.zper, rint(sz * sc.inv_zper), sz);
+        if (PZ) sz = fma(-sc.zper, rint(sz * sc.inv_zper), sz);
         const double r2s = fma(sz, sz, fma(sy, sy, sx * sx));
         if (r2s < sc.rc2s) hits |= 1u << k;
     }
@@ -74,7 +74,7 @@ __device__ __forceinline__ unsigned screen_slots(const Box &b, const ScreenConst
 
 // two points against the same slots in one loop (old and proposed position): 16
 // independent pair evaluations for the scheduler to interleave
-template <int K>
+template <int K, bool PZ>
 __device__ __forceinline__ void screen_slots2(const Box &b, const ScreenConsts &sc,
                                               double ax, double ay, double az, double bx, double by, double bz,
                                               const double (&xs)[K], const double (&ys)[K], const double (&zs)[K],
@@ -86,7 +86,7 @@ __device__ __forceinline__ void screen_slots2(const Box &b, const ScreenConsts &
         const double sxa = wrap_unit_x(ax - xs[k]), sxb = wrap_unit_x(bx - xs[k]);
         const double sya = wrap_unit_y(ay - ys[k]), syb = wrap_unit_y(by - ys[k]);
         double sza = az - zs[k], szb = bz - zs[k];
-        if (b.pz) {
+        if (PZ) {
             sza = fma(-sc.zper, rint(sza * sc.inv_zper), sza);
             szb = fma(-sc.zper, rint(szb * sc.inv_zper), szb);
         }
@@ -167,13 +167,13 @@ __device__ __forceinline__ void add_zwall(const Box &b, double dzw, double &e, d
 
 // energy (already *4) and force of a particle at p against everything else; `in`
 // receives the lane's exact in-cutoff slots.  All lanes return the warp totals.
-template <int K>
+template <int K, bool PZ>
 __device__ __forceinline__ void eval_point(const Box &b, const ScreenConsts &sc, const ChainSmem &s, int lane, int MMpad,
                                            unsigned okmask, double px, double py, double pz,
                                            const double (&xs)[K], const double (&ys)[K], const double (&zs)[K],
                                            double &U, double &Fx, double &Fy, double &Fz, unsigned &in)
 {
-    unsigned hits = screen_slots<K>(b, sc, px * b.invL, py * b.invL, pz * b.invL, xs, ys, zs) & okmask;
+    unsigned hits = screen_slots<K, PZ>(b, sc, px * b.invL, py * b.invL, pz * b.invL, xs, ys, zs) & okmask;
     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
     in = add_hits(b, s, lane, hits, px, py, pz, e, fx, fy, fz);
     double dzw = 0.0;
@@ -187,10 +187,10 @@ __device__ __forceinline__ void eval_point(const Box &b, const ScreenConsts &sc,
 }
 
 #ifndef SMCB_SWEEP_MINB
-#define SMCB_SWEEP_MINB 14
+#define SMCB_SWEEP_MINB 10
 #endif
-template <int K, bool FED>
-__global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_cached(DevChains d, SweepArgs a)
+template <int K, bool FED, bool PZ>
+__device__ __forceinline__ void sweep_cached_body(const DevChains &d, const SweepArgs &a)
 {
     const int lane = threadIdx.x, chain = blockIdx.x;
     const int N = d.N, Npad = d.Npad;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_ca
         const unsigned okmask = validmask & ~(((n & 31) == lane) ? (1u << (n >> 5)) : 0u);
         double U, Fx, Fy, Fz;
         unsigned in;
-        eval_point<K>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], xs, ys, zs, U, Fx, Fy, Fz, in);
+        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], xs, ys, zs, U, Fx, Fy, Fz, in);
         const int cntn = __reduce_add_sync(FULL, __popc(in));
         if (lane == 0) { s.ce[n] = U; s.cfx[n] = Fx; s.cfy[n] = Fy; s.cfz[n] = Fz; s.nb[n] = (unsigned short)cntn; }
     }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_ca
                         qx = min_image<false>(s.x[n] + dX, b.L, b.invL);
                         qy = min_image<false>(s.y[n] + dY, b.L, b.invL);
                         qz = s.z[n] + dZ;
-                        if (b.pz) qz = min_image<false>(qz, b.Lz, b.invLz);
+                        if (PZ) qz = min_image<false>(qz, b.Lz, b.invLz);
                     }
                     const double qsx = qx * b.invL, qsy = qy * b.invL, qsz = qz * b.invL;
 
@@ -332,11 +332,11 @@ __global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_ca
                     // one pass: the proposed position (always) and the old one (only if it has partners)
                     unsigned hits_new, hits_old = 0;
                     if (nbm) {
-                        screen_slots2<K>(b, sc, qsx, qsy, qsz, s.x[n] * b.invL, s.y[n] * b.invL, s.z[n] * b.invL,
+                        screen_slots2<K, PZ>(b, sc, qsx, qsy, qsz, s.x[n] * b.invL, s.y[n] * b.invL, s.z[n] * b.invL,
                                          xs, ys, zs, hits_new, hits_old);
                         hits_old &= okmask;
                     } else {
-                        hits_new = screen_slots<K>(b, sc, qsx, qsy, qsz, xs, ys, zs);
+                        hits_new = screen_slots<K, PZ>(b, sc, qsx, qsy, qsz, xs, ys, zs);
                     }
                     hits_new &= okmask;
 
@@ -441,6 +441,16 @@ __global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_ca
             atomicAdd(d.pair_counts + 1, tot);
         }
     }
+}
+
+
+// PZ (bulk, z periodic) is a per-chain flag: one uniform branch per CTA picks the specialisation, so
+// the slab-mode pair loop carries no predicated-off z-wrap instructions.
+template <int K, bool FED>
+__global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_cached(DevChains d, SweepArgs a)
+{
+    if (chain_params(d, blockIdx.x).flags & SMCB_PERIODIC_Z) sweep_cached_body<K, FED, true>(d, a);
+    else sweep_cached_body<K, FED, false>(d, a);
 }
 
 }  // namespace smcb
