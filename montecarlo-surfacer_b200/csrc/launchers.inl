@@ -35,10 +35,12 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
     if (fed) {
         auto kern = k_sweep_cached<K, true>;
         if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return err;
         kern<<<d.C, 32, smem, st>>>(d, a);
     } else {
         auto kern = k_sweep_cached<K, false>;
         if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return err;
         kern<<<d.C, 32, smem, st>>>(d, a);
     }
 #endif
