@@ -7,7 +7,12 @@ implementation: importing works without a GPU (so the C-ABI export check can run
 Engine does not.
 """
 from .engine import (FAST, STRICT, WALL, PERIODIC_Z, ChainParams, Engine, ObsLayout, SmcbError,
-                     default_params, lib_path, load_library, exported_symbols, header_symbols)
+                     default_params, lib_path, load_library, exported_symbols, header_symbols,
+                     obs_layout_host, unpack_obs)
+from .shard import (Shard, shard_chains, grid_points, grid_chain_params, allreduce_observables,
+                    max_over_ranks)
 
 __all__ = ["FAST", "STRICT", "WALL", "PERIODIC_Z", "ChainParams", "Engine", "ObsLayout", "SmcbError",
-           "default_params", "lib_path", "load_library", "exported_symbols", "header_symbols"]
+           "default_params", "lib_path", "load_library", "exported_symbols", "header_symbols",
+           "obs_layout_host", "unpack_obs", "Shard", "shard_chains", "grid_points", "grid_chain_params",
+           "allreduce_observables", "max_over_ranks"]

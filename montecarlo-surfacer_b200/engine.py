@@ -332,6 +332,14 @@ class Engine:
         return self.lib.smcb_stream(self._h)
 
 
+def obs_layout_host(ngroups, nebins=64, e_lo=-8.0, e_hi=2.0):
+    """the layout smcb_obs_layout_get reports, computed on the host (no engine needed): per group
+    D[33^3] Mu[33^3] zprof[33] ehist[nebins] nsamples | sumE sumE2 sumP sumP2 sumAcc"""
+    nvox, nz = 33 * 33 * 33, 33
+    u64 = 2 * nvox + nz + nebins + 1
+    return ObsLayout(ngroups, nvox, nz, nebins, e_lo, e_hi, u64, 5, u64 * ngroups, 5 * ngroups)
+
+
 def unpack_obs(lay, cnt, mom):
     """split the packed observable block (smcb_obs_layout) into named arrays per group"""
     groups = []
