@@ -18,6 +18,8 @@
  *     text).  There is NO CPU fallback: without a CUDA device smcb_create fails.
  *   - calls on one handle are serialised by the caller; different handles are
  *     independent.  All calls are synchronous on return.
+ *   - no identifier below collides with the reference's macros (N, M, a0, b0, rank, Ncx, Ncz,
+ *     KMAX ...: SMC.h:26-61), so a translation unit built on SMC.h can include this header.
  */
 #ifndef SMCB200_H
 #define SMCB200_H
@@ -59,7 +61,7 @@ typedef struct smcb_chain_params {
     double T;        /* temperature                                                  */
     double A;        /* SMC step parameter: drift A/T * F, noise variance 2A         */
     double rc2;      /* LJ cutoff squared (9.0 in the reference)                     */
-    double a0, b0;   /* flat z-wall 12-6 coefficients                                */
+    double zwall_a, zwall_b;  /* flat z-wall 12-6 coefficients (the a0, b0 macros of SMC.h:32-33) */
     uint32_t flags;  /* SMCB_WALL | SMCB_PERIODIC_Z                                  */
     uint32_t wall;   /* index of this chain's wall table (0 .. nwalls-1)             */
     uint32_t group;  /* observable group (parameter-grid point) this chain adds to   */
@@ -67,8 +69,9 @@ typedef struct smcb_chain_params {
 } smcb_chain_params;
 
 /* ---- lifetime ----------------------------------------------------------- */
-/* nchains chains of N particles, wall tables of M*M sites, on CUDA `device`. */
-int smcb_create(smcb_engine **out, int device, int nchains, int N, int M);
+/* nchains chains of nparticles (the reference's N) molecules, wall tables of nsites_side^2 (M*M)
+ * sites, on CUDA `device`. */
+int smcb_create(smcb_engine **out, int device, int nchains, int nparticles, int nsites_side);
 int smcb_destroy(smcb_engine *e);
 const char *smcb_last_error(void);
 /* library / device facts: "sm_100a", SM count, etc. (for logs and tests) */
@@ -118,6 +121,12 @@ int smcb_sweep_fed(smcb_engine *e, int nsweeps, int mode,
                    const double *displ, const int64_t *offset, const double *u,
                    uint8_t *accepted);
 int smcb_sweep(smcb_engine *e, int nsweeps, int mode);
+/* same, and returns what sMC records after every sweep (SMC.c:116-117, 194-195): the running
+ * energy E_trace[s][c] (sMC's E[n+1]) and the accepted trials of that sweep acc_trace[s][c] (jj[n]).
+ * displ/offset/u: all NULL (Philox) or all given (host-fed, as smcb_sweep_fed). */
+int smcb_sweep_traced(smcb_engine *e, int nsweeps, int mode,
+                      const double *displ, const int64_t *offset, const double *u,
+                      double *E_trace, int32_t *acc_trace);
 /* thermalisation helper: sweeps run with A*scale (sMC uses 2, SMC.c:110) */
 int smcb_set_step_scale(smcb_engine *e, double scale);
 
@@ -137,6 +146,9 @@ int smcb_step_allparticle(smcb_engine *e, int nsteps, int mode);
  * naccept / ntrials: accepted and attempted trials since the last reset. */
 int smcb_refresh_energy(smcb_engine *e, int mode);       /* E <- energy + wallsEnergy (SMC.c:48) */
 int smcb_get_chain_state(smcb_engine *e, double *E, int64_t *naccept, int64_t *ntrials);
+/* caller-provided running energies, nchains doubles (sMC seeds E[0] itself, SMC.c:48, and carries
+ * E[n+1] = E[n] into every sweep, SMC.c:116,194) */
+int smcb_set_chain_energy(smcb_engine *e, const double *E);
 int smcb_reset_counters(smcb_engine *e);
 
 /* ---- observables (row a13 + what sMC harvests, SMC.c:137-141) ------------
@@ -170,6 +182,7 @@ int smcb_obs_export_device(smcb_engine *e, void *counters_dev, void *moments_dev
 int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void *moments_dev);
 /* per-chain Rbin (voxel of each particle at the last gather), nchains*N ints */
 int smcb_get_rbin(smcb_engine *e, int32_t *rbin);
+int smcb_set_rbin(smcb_engine *e, const int32_t *rbin);
 
 /* ---- measurement -------------------------------------------------------- */
 /* device time (ms, CUDA events on the engine's stream) of the kernels launched

@@ -64,7 +64,8 @@ struct smcb_engine {
     DevBuf<long long> nacc, ntri, fed_off;
     DevBuf<unsigned long long> pairs, counters;
     DevBuf<unsigned char> fed_acc;
-    DevBuf<int> rbin;
+    DevBuf<int> rbin, trace_acc;
+    DevBuf<double> trace_E;
     uint64_t seed = 0x5eed5eedull, step = 0;
     uint32_t chain0 = 0;
     double step_scale = 1.0;
@@ -157,7 +158,7 @@ int smcb_destroy(smcb_engine *e)
     e->F.release(); e->Fn.release(); e->dl.release(); e->e_lj.release(); e->f_lj.release();
     e->e_wall.release(); e->f_wall.release(); e->totals.release(); e->moments.release();
     e->peak_out.release(); e->fed_a.release(); e->fed_b.release(); e->nacc.release(); e->ntri.release();
-    e->cache_out.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
+    e->cache_out.release(); e->trace_E.release(); e->trace_acc.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -377,6 +378,17 @@ int smcb_get_chain_state(smcb_engine *e, double *E, int64_t *naccept, int64_t *n
     return SMCB_OK;
 }
 
+int smcb_set_chain_energy(smcb_engine *e, const double *E)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!E) return fail(SMCB_ERR_ARG, "E is null");
+    CK(cudaMemcpyAsync(e->E.p, E, e->C * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->energy_valid = true;
+    return SMCB_OK;
+}
+
 int smcb_reset_counters(smcb_engine *e)
 {
     int rc = check(e);
@@ -399,7 +411,8 @@ static int finish_timed(smcb_engine *e, int launches)
 }
 
 static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const double *displ,
-                        const int64_t *offset, const double *u, uint8_t *accepted)
+                        const int64_t *offset, const double *u, uint8_t *accepted,
+                        double *E_trace = nullptr, int32_t *acc_trace = nullptr)
 {
     int rc = need_ready(e);
     if (rc) return rc;
@@ -423,6 +436,11 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
         a.displ = e->fed_a.p; a.u = e->fed_b.p; a.offset = e->fed_off.p;
         if (accepted) { CK(e->fed_acc.ensure(sc * e->N)); a.accepted = e->fed_acc.p; }
     }
+    const bool traced = E_trace != nullptr || acc_trace != nullptr;
+    if (traced) {
+        CK(e->trace_E.ensure(sc)); CK(e->trace_acc.ensure(sc));
+        a.trace_E = e->trace_E.p; a.trace_acc = e->trace_acc.p;
+    }
     if (e->capture_cache && mode == SMCB_FAST) {
         CK(e->cache_out.ensure((size_t)e->C * 5 * e->Npad));
         a.cache_out = e->cache_out.p;
@@ -434,6 +452,11 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
     if ((rc = finish_timed(e, 1))) return rc;
     if (fed && accepted) {
         CK(cudaMemcpyAsync(accepted, e->fed_acc.p, sc * e->N, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    if (traced) {
+        if (E_trace) CK(cudaMemcpyAsync(E_trace, e->trace_E.p, sc * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (acc_trace) CK(cudaMemcpyAsync(acc_trace, e->trace_acc.p, sc * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
     if (!fed) e->step += (uint64_t)nsweeps;
@@ -450,6 +473,13 @@ int smcb_sweep_fed(smcb_engine *e, int nsweeps, int mode, const double *displ, c
 int smcb_sweep(smcb_engine *e, int nsweeps, int mode)
 {
     return sweep_common(e, nsweeps, mode, false, nullptr, nullptr, nullptr, nullptr);
+}
+
+int smcb_sweep_traced(smcb_engine *e, int nsweeps, int mode, const double *displ, const int64_t *offset,
+                      const double *u, double *E_trace, int32_t *acc_trace)
+{
+    const bool fed = displ || offset || u;
+    return sweep_common(e, nsweeps, mode, fed, displ, offset, u, nullptr, E_trace, acc_trace);
 }
 
 // ------------------------------------------------------- all-particle step
@@ -599,6 +629,16 @@ int smcb_get_rbin(smcb_engine *e, int32_t *rbin)
     if (rc) return rc;
     if (!rbin) return fail(SMCB_ERR_ARG, "rbin is null");
     CK(cudaMemcpyAsync(rbin, e->rbin.p, (size_t)e->C * e->N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+int smcb_set_rbin(smcb_engine *e, const int32_t *rbin)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!rbin) return fail(SMCB_ERR_ARG, "rbin is null");
+    CK(cudaMemcpyAsync(e->rbin.p, rbin, (size_t)e->C * e->N * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return SMCB_OK;
 }

@@ -49,6 +49,8 @@ struct SweepArgs {
     const double *u;           // FED: [s][C][N]
     unsigned char *accepted;   // FED, nullable: [s][C][N]
     double *cache_out;         // test hook of the cached kernel, nullable: [C][5][Npad]
+    double *trace_E;           // nullable [s][C]: running energy after every sweep (sMC's E[n+1], SMC.c:116,194)
+    int *trace_acc;            // nullable [s][C]: accepted trials of every sweep (sMC's jj[n])
 };
 
 struct StepArgs {
@@ -476,6 +478,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
     for (int s = 0; s < a.nsweeps; s++) {
         const unsigned long long step = a.rng.step0 + (unsigned long long)s;
         const size_t sc = (size_t)s * d.C + chain;
+        const long long nacc0 = nacc;
         long long offset;                              // int offset = rand();  SMC.c:290
         if (FED) {
             offset = a.offset[sc];
@@ -561,6 +564,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
                 __syncwarp();
             }
         }
+        if (a.trace_E != nullptr && lane == 0) { a.trace_E[sc] = E; a.trace_acc[sc] = (int)(nacc - nacc0); }
     }
 
     for (int j = lane; j < N; j += 32) {               // the shared-memory mirror holds the exact positions

@@ -30,7 +30,7 @@ __device__ __forceinline__ Box make_box(const smcb_chain_params &p, int M, doubl
 {
     Box b;
     b.L = p.L; b.Lz = p.Lz; b.invL = 1.0 / p.L; b.invLz = 1.0 / p.Lz;
-    b.rc2 = p.rc2; b.a0 = p.a0; b.b0 = p.b0; b.T = p.T; b.A = p.A * step_scale;
+    b.rc2 = p.rc2; b.a0 = p.zwall_a; b.b0 = p.zwall_b; b.T = p.T; b.A = p.A * step_scale;
     b.wall = (p.flags & SMCB_WALL) != 0; b.pz = (p.flags & SMCB_PERIODIC_Z) != 0;
     b.M = M;
     return b;

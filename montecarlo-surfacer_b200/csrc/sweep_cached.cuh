@@ -267,6 +267,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
     for (int sw = 0; sw < a.nsweeps; sw++) {
         const unsigned long long step = a.rng.step0 + (unsigned long long)sw;
         const size_t sci = (size_t)sw * d.C + chain;
+        const int nacc0 = nacc;
         long long offset;                              // int offset = rand();  SMC.c:290
         if (FED) {
             offset = a.offset[sci];
@@ -417,6 +418,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
             }
             if (seg < K) rotate();
         }
+        if (a.trace_E != nullptr && lane == 0) { a.trace_E[sci] = E; a.trace_acc[sci] = nacc - nacc0; }
     }
 
     for (int j = lane; j < N; j += 32) {               // the shared-memory mirror holds the exact positions

@@ -25,7 +25,7 @@ class SmcbError(RuntimeError):
 class ChainParams(C.Structure):
     """smcb_chain_params"""
     _fields_ = [("L", C.c_double), ("Lz", C.c_double), ("T", C.c_double), ("A", C.c_double),
-                ("rc2", C.c_double), ("a0", C.c_double), ("b0", C.c_double),
+                ("rc2", C.c_double), ("zwall_a", C.c_double), ("zwall_b", C.c_double),
                 ("flags", C.c_uint32), ("wall", C.c_uint32), ("group", C.c_uint32), ("pad_", C.c_uint32)]
 
 
@@ -75,11 +75,14 @@ def load_library():
         "smcb_evaluate": [P, C.c_int] + [P] * 8,
         "smcb_sweep_fed": [P, C.c_int, C.c_int, P, P, P, P],
         "smcb_sweep": [P, C.c_int, C.c_int],
+        "smcb_sweep_traced": [P, C.c_int, C.c_int, P, P, P, P, P],
+        "smcb_set_rbin": [P, P],
         "smcb_set_step_scale": [P, C.c_double],
         "smcb_step_allparticle_fed": [P, C.c_int, C.c_int, P, P, P, P],
         "smcb_step_allparticle": [P, C.c_int, C.c_int],
         "smcb_refresh_energy": [P, C.c_int],
         "smcb_get_chain_state": [P, P, P, P],
+        "smcb_set_chain_energy": [P, P],
         "smcb_reset_counters": [P],
         "smcb_obs_configure": [P, C.c_int, C.c_double, C.c_double],
         "smcb_obs_layout_get": [P, C.POINTER(ObsLayout)],
@@ -239,6 +242,16 @@ class Engine:
     def sweep(self, nsweeps, mode=FAST):
         self._ck(self.lib.smcb_sweep(self._h, nsweeps, mode))
 
+    def sweep_traced(self, nsweeps, mode=FAST, displ=None, offset=None, u=None):
+        """(E_trace [S,C], acc_trace [S,C]): sMC's E[n+1] and jj[n] of every sweep"""
+        Et = np.empty((nsweeps, self.C))
+        at = np.empty((nsweeps, self.C), dtype=np.int32)
+        if displ is not None:
+            displ, u = _f64(displ, nsweeps * self.C * 3 * self.N), _f64(u, nsweeps * self.C * self.N)
+            offset = np.ascontiguousarray(offset, dtype=np.int64)
+        self._ck(self.lib.smcb_sweep_traced(self._h, nsweeps, mode, _ptr(displ), _ptr(offset), _ptr(u), _ptr(Et), _ptr(at)))
+        return Et, at
+
     # -- the all-particle step -----------------------------------------------------
     def step_allparticle_fed(self, xi, u, mode=FAST):
         """xi [S,C,3N] (already scaled by sqrt(2A)), u [S,C]; returns (lnap [S,C], accepted [S,C])"""
@@ -263,6 +276,10 @@ class Engine:
         nt = np.empty(self.C, dtype=np.int64)
         self._ck(self.lib.smcb_get_chain_state(self._h, _ptr(E), _ptr(na), _ptr(nt)))
         return E, na, nt
+
+    def set_chain_energy(self, E):
+        E = _f64(E, self.C)
+        self._ck(self.lib.smcb_set_chain_energy(self._h, _ptr(E)))
 
     def reset_counters(self):
         self._ck(self.lib.smcb_reset_counters(self._h))
@@ -300,6 +317,10 @@ class Engine:
         rb = np.empty((self.C, self.N), dtype=np.int32)
         self._ck(self.lib.smcb_get_rbin(self._h, _ptr(rb)))
         return rb
+
+    def set_rbin(self, rb):
+        rb = np.ascontiguousarray(rb, dtype=np.int32)
+        self._ck(self.lib.smcb_set_rbin(self._h, _ptr(rb)))
 
     # -- measurement -----------------------------------------------------------------
     def last_kernel_ms(self):

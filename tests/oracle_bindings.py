@@ -201,11 +201,14 @@ class Oracle:
 class RefLib:
     """The compiled reference for one (N, M).  Functions keep the reference's names."""
 
-    def __init__(self, N, M=3, fast=False):
-        tag = f"libref_N{N}_M{M}" + ("_fast" if fast else "") + ".so"
-        path = os.path.join(ORACLE_DIR, "_ref", tag)
+    def __init__(self, N, M=3, fast=False, path=None):
+        """path: another library exporting the same SMC.h API (the drop-in, tests/dropin/_build)"""
+        if path is None:
+            tag = f"libref_N{N}_M{M}" + ("_fast" if fast else "") + ".so"
+            path = os.path.join(ORACLE_DIR, "_ref", tag)
         if not os.path.exists(path):
-            raise FileNotFoundError(f"{path} missing: run oracle/build_ref.sh where /root/reference exists")
+            raise FileNotFoundError(f"{path} missing: run oracle/build_ref.sh where /root/reference exists "
+                                    "(or make -C tests/dropin for the drop-in)")
         self.N, self.M = N, M
         L = self.lib = C.CDLL(path)
         assert L.ref_N() == N and L.ref_M() == M
