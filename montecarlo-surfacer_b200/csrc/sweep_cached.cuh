@@ -35,64 +35,118 @@ struct ChainSmem {
     double *ce, *cfx, *cfy, *cfz;   // cached per-particle energy and force (LJ + surface)
     unsigned short *nb;       // cached number of LJ partners inside the cutoff
     double *site;             // [4][MMpad]: site x, y, a, b
+    float *stage;             // [3][32]: speculative proposals of the slot being visited, in box units (screen precision)
     __device__ __forceinline__ void carve(double *base, int Npad, int MMpad)
     {
         x = base; y = x + Npad; z = y + Npad;
         ce = z + Npad; cfx = ce + Npad; cfy = cfx + Npad; cfz = cfy + Npad;
         site = cfz + Npad;
-        nb = reinterpret_cast<unsigned short *>(site + 4 * MMpad);
+        stage = reinterpret_cast<float *>(site + 4 * MMpad);
+        nb = reinterpret_cast<unsigned short *>(stage + 3 * 32);
     }
     static __host__ __device__ size_t bytes(int Npad, int MMpad)
     {
-        return (size_t)(7 * Npad + 4 * MMpad) * sizeof(double) + (size_t)Npad * sizeof(unsigned short);
+        return (size_t)(7 * Npad + 4 * MMpad) * sizeof(double) + (size_t)(3 * 32) * sizeof(float) + (size_t)Npad * sizeof(unsigned short);
     }
 };
 
+// ---- phase 1: the screen, in packed single precision ---------------------------------------------
+// The screen only has to find a SUPERSET of the partners inside the cutoff: every hit is re-tested and
+// evaluated in double precision from the exact positions (pair_exact), and a pair outside the cutoff
+// contributes exactly 0, so the results do not depend on the screen's precision.  On B200 the FP64 pipe
+// issues one warp instruction per 2 cycles and is the scarce resource (profiles/r01: screen_thr.txt):
+// an 8-slot FP64 screen costs ~224 SM-sub-partition cycles, the packed FP32 one ~130.  Positions are kept
+// in box units (x/L) as float2 pairs of slots; a minimum image is s - rint(s) with the 1.5*2^23 trick, and
+// add/sub/mul/fma.f32x2 (FADD2/FMUL2/FFMA2, sm_100+) work on two slots per instruction.
 struct ScreenConsts {
-    double rc2s;              // rc2 / L^2, inflated by 1e-12 (phase-1 screen; exact test in phase 2)
-    double zper, inv_zper;    // Lz/L and L/Lz (bulk mode only)
+    float rc2s;               // (rc/L + margin)^2: cutoff in box units, inflated by the FP32 error bound below
+    float zper, inv_zper;     // Lz/L and L/Lz (bulk mode only)
 };
 
-// phase 1: which of the lane's K slots are within the (slightly inflated) cutoff of the
-// point (psx,psy,psz) given in box units
-template <int K, bool PZ>
-__device__ __forceinline__ unsigned screen_slots(const Box &b, const ScreenConsts &sc, double psx, double psy, double psz,
-                                                 const double (&xs)[K], const double (&ys)[K], const double (&zs)[K])
+// FP32 error bound of a box-unit separation: operands are rounded to float (|x|,|y| <= 1/2, |z| <= Lz/L
+// allowing excursions), differences and the wrap add one more rounding each.  Four times that bound is
+// added to the cutoff RADIUS, so a pair inside the true cutoff can never be screened out.
+__device__ __forceinline__ ScreenConsts make_screen(const Box &b)
 {
-    unsigned hits = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const double sx = wrap_unit_x(psx - xs[k]);
-        const double sy = wrap_unit_y(psy - ys[k]);
-        double sz = psz - zs[k];
-        if (PZ) sz = fma(-sc.zper, rint(sz * sc.inv_zper), sz);
-        const double r2s = fma(sz, sz, fma(sy, sy, sx * sx));
-        if (r2s < sc.rc2s) hits |= 1u << k;
-    }
-    return hits;
+    const double eps = 1.1920929e-7;                       // 2^-23
+    const double zmax = b.Lz * b.invL + 1.0;
+    const double delta = eps * (2.0 + 2.0 * zmax);
+    const double rcs = sqrt(b.rc2) * b.invL + 4.0 * delta;
+    ScreenConsts sc;
+    sc.rc2s = (float)(rcs * rcs * (1.0 + 1e-6));
+    sc.zper = (float)(b.Lz * b.invL); sc.inv_zper = (float)(b.L * b.invLz);
+    return sc;
 }
 
-// two points against the same slots in one loop (old and proposed position): 16
-// independent pair evaluations for the scheduler to interleave
-template <int K, bool PZ>
-__device__ __forceinline__ void screen_slots2(const Box &b, const ScreenConsts &sc,
-                                              double ax, double ay, double az, double bx, double by, double bz,
-                                              const double (&xs)[K], const double (&ys)[K], const double (&zs)[K],
-                                              unsigned &hits_a, unsigned &hits_b)
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
 {
-    hits_a = hits_b = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const double sxa = wrap_unit_x(ax - xs[k]), sxb = wrap_unit_x(bx - xs[k]);
-        const double sya = wrap_unit_y(ay - ys[k]), syb = wrap_unit_y(by - ys[k]);
-        double sza = az - zs[k], szb = bz - zs[k];
-        if (PZ) {
-            sza = fma(-sc.zper, rint(sza * sc.inv_zper), sza);
-            szb = fma(-sc.zper, rint(szb * sc.inv_zper), szb);
-        }
-        if (fma(sza, sza, fma(sya, sya, sxa * sxa)) < sc.rc2s) hits_a |= 1u << k;
-        if (fma(szb, szb, fma(syb, syb, sxb * sxb)) < sc.rc2s) hits_b |= 1u << k;
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+
+// the lane's K particles (slots), box units, packed two slots per float2; odd K pads with a far-away slot
+template <int K>
+struct Slots {
+    static constexpr int KP = (K + 1) / 2;
+    float2 x[KP], y[KP], z[KP];
+    __device__ __forceinline__ void set(int k, float X, float Y, float Z)       // k is a compile-time constant at every call site
+    {
+        if (k & 1) { x[k >> 1].y = X; y[k >> 1].y = Y; z[k >> 1].y = Z; }
+        else       { x[k >> 1].x = X; y[k >> 1].x = Y; z[k >> 1].x = Z; }
     }
+    __device__ __forceinline__ void get(int k, float &X, float &Y, float &Z) const
+    {
+        if (k & 1) { X = x[k >> 1].y; Y = y[k >> 1].y; Z = z[k >> 1].y; }
+        else       { X = x[k >> 1].x; Y = y[k >> 1].x; Z = z[k >> 1].x; }
+    }
+};
+
+// which of the lane's K slots are within the (inflated) cutoff of the point (px,py,pz), box units
+template <int K, bool PZ>
+__device__ __forceinline__ unsigned screen_slots(const ScreenConsts &sc, float px, float py, float pz, const Slots<K> &q)
+{
+    const float2 ax = make_float2(px, px), ay = make_float2(py, py), az = make_float2(pz, pz);
+    const float2 MG = make_float2(12582912.f, 12582912.f);           // 1.5 * 2^23: (s + MG) - MG = rint(s)
+    unsigned hits = 0;
+#pragma unroll
+    for (int k = 0; k < Slots<K>::KP; k++) {
+        float2 sx = sub2(ax, q.x[k]);
+        sx = sub2(sx, sub2(add2(sx, MG), MG));
+        float2 sy = sub2(ay, q.y[k]);
+        sy = sub2(sy, sub2(add2(sy, MG), MG));
+        float2 sz = sub2(az, q.z[k]);
+        if (PZ) {
+            const float2 t = mul2(sz, make_float2(sc.inv_zper, sc.inv_zper));
+            sz = fma2(sub2(add2(t, MG), MG), make_float2(-sc.zper, -sc.zper), sz);
+        }
+        const float2 r2 = fma2(sz, sz, fma2(sy, sy, mul2(sx, sx)));
+        if (r2.x < sc.rc2s) hits |= 1u << (2 * k);
+        if (r2.y < sc.rc2s) hits |= 2u << (2 * k);
+    }
+    return hits;
 }
 
 // exact 12-6 terms of one pair from unscaled positions (same arithmetic as lj_terms<false,true>
@@ -169,11 +223,10 @@ __device__ __forceinline__ void add_zwall(const Box &b, double dzw, double &e, d
 // receives the lane's exact in-cutoff slots.  All lanes return the warp totals.
 template <int K, bool PZ>
 __device__ __forceinline__ void eval_point(const Box &b, const ScreenConsts &sc, const ChainSmem &s, int lane, int MMpad,
-                                           unsigned okmask, double px, double py, double pz,
-                                           const double (&xs)[K], const double (&ys)[K], const double (&zs)[K],
+                                           unsigned okmask, double px, double py, double pz, const Slots<K> &q,
                                            double &U, double &Fx, double &Fy, double &Fz, unsigned &in)
 {
-    unsigned hits = screen_slots<K, PZ>(b, sc, px * b.invL, py * b.invL, pz * b.invL, xs, ys, zs) & okmask;
+    unsigned hits = screen_slots<K, PZ>(sc, (float)(px * b.invL), (float)(py * b.invL), (float)(pz * b.invL), q) & okmask;
     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
     in = add_hits(b, s, lane, hits, px, py, pz, e, fx, fy, fz);
     double dzw = 0.0;
@@ -203,7 +256,8 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
     const double *W = d.W + (size_t)cp.wall * 2 * MM;
     double *P = d.pos + (size_t)chain * 3 * Npad;
 
-    double xs[K], ys[K], zs[K];
+    Slots<K> q;
+    if (K & 1) q.set(K, 0.f, 0.f, 3.0e18f);              // pad slot of an odd K: never within the cutoff
     unsigned validmask = 0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -211,7 +265,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
         const bool in = j < N;
         const double X = in ? P[j] : 0.0, Y = in ? P[Npad + j] : 0.0, Z = in ? P[2 * Npad + j] : 0.0;
         if (j < Npad) { s.x[j] = X; s.y[j] = Y; s.z[j] = Z; }
-        xs[k] = X * b.invL; ys[k] = Y * b.invL; zs[k] = Z * b.invL;
+        q.set(k, (float)(X * b.invL), (float)(Y * b.invL), (float)(Z * b.invL));
         if (in) validmask |= 1u << k;
     }
     if (b.wall) {
@@ -223,16 +277,14 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
         }
     }
     __syncwarp();
-    ScreenConsts sc;
-    sc.rc2s = b.rc2 * b.invL * b.invL * (1.0 + 1e-12);
-    sc.zper = b.Lz * b.invL; sc.inv_zper = b.L * b.invLz;
+    const ScreenConsts sc = make_screen(b);
 
     // ---- rebuild the caches from the positions ------------------------------------
     for (int n = 0; n < N; n++) {
         const unsigned okmask = validmask & ~(((n & 31) == lane) ? (1u << (n >> 5)) : 0u);
         double U, Fx, Fy, Fz;
         unsigned in;
-        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], xs, ys, zs, U, Fx, Fy, Fz, in);
+        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], q, U, Fx, Fy, Fz, in);
         const int cntn = __reduce_add_sync(FULL, __popc(in));
         if (lane == 0) { s.ce[n] = U; s.cfx[n] = Fx; s.cfy[n] = Fy; s.cfz[n] = Fz; s.nb[n] = (unsigned short)cntn; }
     }
@@ -242,6 +294,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
     const double sigma = sqrt(2.0 * b.A);            // vecBoxMuller(sqrt(2.0*A), ...)  SMC.c:284
     const double quarterAoT = 0.25 * AoT, invT = 1.0 / b.T;
     double E = d.E[chain];
+    double dE = 0.0;                                 // per-lane share of the running energy (speculative path)
     int nacc = 0;
     unsigned cnt = 0;                                // per-lane, < 2^32 per launch
     const RngId id{a.rng.k0, a.rng.k1, a.rng.chain0 + (uint32_t)chain};
@@ -253,10 +306,11 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
     int rot = 0;
     auto rotate = [&]() {
         if (K > 1) {
-            const double tx = xs[0], ty = ys[0], tz = zs[0];
+            float tx, ty, tz, ux, uy, uz;
+            q.get(0, tx, ty, tz);
 #pragma unroll
-            for (int k = 0; k + 1 < K; k++) { xs[k] = xs[k + 1]; ys[k] = ys[k + 1]; zs[k] = zs[k + 1]; }
-            xs[K - 1] = tx; ys[K - 1] = ty; zs[K - 1] = tz;
+            for (int k = 0; k + 1 < K; k++) { q.get(k + 1, ux, uy, uz); q.set(k, ux, uy, uz); }
+            q.set(K - 1, tx, ty, tz);
             validmask = (validmask >> 1) | ((validmask & 1u) << (K - 1));
             rot = (rot + 1 == K) ? 0 : rot + 1;
         }
@@ -286,10 +340,20 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
             int te = min(32, N - 32 * slot);            // particles of this slot that exist
             if (seg == K) te = min(te, t0);
             if (tb < te) {
-                // each lane prepares the random inputs of its own particle of this slot
+                // Each lane prepares its own particle of this slot (lane <-> particle 32*slot+lane): the random
+                // inputs, and SPECULATIVELY the whole trial under the assumption that nobody is in range of the
+                // proposal - proposal from the cached force, flat-wall terms there, acceptance.  That is the
+                // common case in the gas phase, and there a trial costs only the O(N) screen below.  The
+                // speculation of lane t is void ("slow") when its particle has partners at the old position,
+                // when the proposal comes within the cutoff of the surface, when the screen finds a partner, or
+                // when an earlier accepted trial of this segment touched its caches (dirty).
                 const int nl = 32 * slot + lane;
+                const bool mine = lane >= tb && lane < te;
+                __syncwarp();                           // the previous segment is done with the staging area
                 double g0 = 0.0, g1 = 0.0, g2 = 0.0, lul = 0.0;
-                if (lane >= tb && lane < te) {
+                double p_qx = 0.0, p_qy = 0.0, p_qz = 0.0, p_Un = 0.0, p_fz = 0.0, p_dU = 0.0;
+                bool p_slow = false, p_acc = false;
+                if (mine) {
                     double ul;
                     if (FED) {
                         const double *dsp = a.displ + sci * 3 * N;
@@ -303,10 +367,60 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                         ul = rng_particle_uniform(id, step, (uint32_t)nl);
                     }
                     lul = log(ul);                      // u < exp(x)  <=>  log(u) < x, evaluated lane-parallel
+                    const double Fmx = s.cfx[nl], Fmy = s.cfy[nl], Fmz = s.cfz[nl], Um = s.ce[nl];
+                    const double dX = fma(Fmx, AoT, g0), dY = fma(Fmy, AoT, g1), dZ = fma(Fmz, AoT, g2);   // SMC.c:307-309
+                    p_qx = min_image<false>(s.x[nl] + dX, b.L, b.invL);                                    // SMC.c:311-316
+                    p_qy = min_image<false>(s.y[nl] + dY, b.L, b.invL);
+                    p_qz = s.z[nl] + dZ;
+                    if (PZ) p_qz = min_image<false>(p_qz, b.Lz, b.invLz);
+                    double ew = 0.0;
+                    bool near = false;
+                    if (b.wall) {
+                        const double dzw = wall_dz<false>(b, p_qz);
+                        near = dzw * dzw < b.rc2;
+                        add_zwall(b, dzw, ew, p_fz);
+                    }
+                    p_Un = 4.0 * ew;                                                                      // SMC.c:319, no partners
+                    const double f2 = p_fz * p_fz - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
+                    const double dr = fma(dX, Fmx, fma(dY, Fmy, dZ * (p_fz + Fmz)));
+                    p_dU = p_Un - Um;
+                    const double xarg = -(p_dU + 0.5 * dr + f2 * quarterAoT) * invT;                      // SMC.c:326-329
+                    p_acc = (lul < xarg) && (xarg > -745.1332191019411);
+                    p_slow = near || s.nb[nl] != 0;
+                    s.stage[lane] = (float)(p_qx * b.invL); s.stage[32 + lane] = (float)(p_qy * b.invL); s.stage[64 + lane] = (float)(p_qz * b.invL);
                 }
+                __syncwarp();
+                const unsigned slow0 = __ballot_sync(FULL, p_slow);
+                const unsigned acc0 = __ballot_sync(FULL, p_acc);
+                unsigned dirty = 0;
                 for (int t = tb; t < te; t++) {
                     const int n = 32 * slot + t;
                     const unsigned okmask = validmask & ~((lane == t) ? 1u : 0u);
+                    if (!(((slow0 | dirty) >> t) & 1u)) {
+                        // ---- speculative path: one screen of the lane's K slots against the staged proposal
+                        const float fsx = s.stage[t], fsy = s.stage[32 + t], fsz = s.stage[64 + t];
+                        const unsigned fh = screen_slots<K, PZ>(sc, fsx, fsy, fsz, q) & okmask;
+                        if (!__any_sync(FULL, fh != 0)) {
+                            const bool facc = (acc0 >> t) & 1u;
+                            if (facc) {
+                                if (lane == t) {         // the owner: its registers hold the proposal and its energy/force
+                                    s.x[n] = p_qx; s.y[n] = p_qy; s.z[n] = p_qz;
+                                    s.ce[n] = p_Un; s.cfx[n] = 0.0; s.cfy[n] = 0.0; s.cfz[n] = p_fz;
+                                    q.set(0, fsx, fsy, fsz);
+                                    dE += p_dU;         // SMC.c:341, summed per lane, reduced at the end of the sweep
+                                }
+                                nacc++;
+                            }
+                            if (FED && a.accepted != nullptr && lane == 0) {
+                                int nn = n - off;
+                                if (nn < 0) nn += N;
+                                a.accepted[sci * N + nn] = facc ? 1 : 0;
+                            }
+                            continue;
+                        }
+                    }
+                    // ---- general path: everything about this trial is (re)computed from the caches as they stand
+                    __syncwarp();
                     const int nbm = s.nb[n];
                     double dX, dY, dZ, qx, qy, qz;
                     {
@@ -319,7 +433,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                         qz = s.z[n] + dZ;
                         if (PZ) qz = min_image<false>(qz, b.Lz, b.invLz);
                     }
-                    const double qsx = qx * b.invL, qsy = qy * b.invL, qsz = qz * b.invL;
+                    const float qsx = (float)(qx * b.invL), qsy = (float)(qy * b.invL), qsz = (float)(qz * b.invL);
 
                     // flat wall at the proposal: uniform, no cutoff; started early, off the pair loop's path
                     double ew = 0.0, fzw = 0.0, dzw = 0.0;
@@ -332,14 +446,9 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
 
                     // one pass: the proposed position (always) and the old one (only if it has partners)
                     unsigned hits_new, hits_old = 0;
-                    if (nbm) {
-                        screen_slots2<K, PZ>(b, sc, qsx, qsy, qsz, s.x[n] * b.invL, s.y[n] * b.invL, s.z[n] * b.invL,
-                                         xs, ys, zs, hits_new, hits_old);
-                        hits_old &= okmask;
-                    } else {
-                        hits_new = screen_slots<K, PZ>(b, sc, qsx, qsy, qsz, xs, ys, zs);
-                    }
-                    hits_new &= okmask;
+                    if (nbm)
+                        hits_old = screen_slots<K, PZ>(sc, (float)(s.x[n] * b.invL), (float)(s.y[n] * b.invL), (float)(s.z[n] * b.invL), q) & okmask;
+                    hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
 
                     // gas-phase fast path: nobody in range of the proposal -> all pair and site sums are exactly 0
                     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
@@ -371,6 +480,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                     cnt += __popc(in_new) + (lane == 0 ? nbm : 0);   // partners at the new + at the old position
                     if (acc) {
                         // partners lose the old pair terms and gain the new ones (force on j from n = -g d)
+                        bool touched = false;           // physical slot 0 = the slot being visited: its speculation is void
                         if (nbm) {
                             const double px = s.x[n], py = s.y[n], pz = s.z[n];
                             while (hits_old) {
@@ -381,6 +491,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                                 if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
                                     s.ce[j] -= 4.0 * et; s.cfx[j] += hx; s.cfy[j] += hy; s.cfz[j] += hz;
                                     s.nb[j] -= 1;
+                                    touched |= (k == 0);
                                 }
                             }
                         }
@@ -395,15 +506,17 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                                 pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz);
                                 s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
                                 s.nb[j] += 1;
+                                touched |= (k == 0);
                             }
                             nbn = __reduce_add_sync(FULL, __popc(in_new));
                         }
+                        dirty |= __ballot_sync(FULL, touched);
                         __syncwarp();                    // partner updates read the old position of n: order before overwriting it
                         if (lane == t) {                 // the owner: physical slot 0 is the visited slot
                             s.x[n] = qx; s.y[n] = qy; s.z[n] = qz;
                             s.ce[n] = Un; s.cfx[n] = Fnx; s.cfy[n] = Fny; s.cfz[n] = Fnz;
                             s.nb[n] = (unsigned short)nbn;
-                            xs[0] = qsx; ys[0] = qsy; zs[0] = qsz;
+                            q.set(0, qsx, qsy, qsz);
                         }
                         E += Un - Um;                   // SMC.c:341
                         nacc++;
@@ -418,6 +531,8 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
             }
             if (seg < K) rotate();
         }
+        E += warp_sum(dE);
+        dE = 0.0;
         if (a.trace_E != nullptr && lane == 0) { a.trace_E[sci] = E; a.trace_acc[sci] = nacc - nacc0; }
     }
 
@@ -448,8 +563,13 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
 
 // PZ (bulk, z periodic) is a per-chain flag: one uniform branch per CTA picks the specialisation, so
 // the slab-mode pair loop carries no predicated-off z-wrap instructions.
+#ifdef SMCB_SWEEP_MAXREG
+#define SMCB_SWEEP_BOUNDS __maxnreg__(SMCB_SWEEP_MAXREG)
+#else
+#define SMCB_SWEEP_BOUNDS __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8))
+#endif
 template <int K, bool FED>
-__global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SWEEP_MINB : 8)) k_sweep_cached(DevChains d, SweepArgs a)
+__global__ void SMCB_SWEEP_BOUNDS k_sweep_cached(DevChains d, SweepArgs a)
 {
     if (chain_params(d, blockIdx.x).flags & SMCB_PERIODIC_Z) sweep_cached_body<K, FED, true>(d, a);
     else sweep_cached_body<K, FED, false>(d, a);
