@@ -1,0 +1,282 @@
+// allparticle_fast.cuh — the FAST all-particle Smart-MC step (north-star kernel B).
+//
+// Every molecule of a chain is displaced at once, d_i = F_i A/T + xi_i, energy and forces are
+// recomputed at the proposal with an O(N^2) pair kernel and ONE Metropolis-Hastings test per chain
+// decides (acceptance expression of SMC.c:326-329 summed over the molecules; the reference's own
+// all-particle attempt, markovProbability, is dead code, SMC.c:354-402).  Forces and energy of the
+// current state are carried from step to step, so a step costs one force evaluation.
+//
+// Organisation for B200:
+//  * CL thread blocks per chain (CL = 1, or a thread-block CLUSTER of CL = 2/4/8 for large N, so
+//    that 32 chains of N = 4096 still fill 148 SMs).  Block `part` owns molecules i = part, part+CL...
+//    strided by thread; every block stages ALL proposal positions of the chain in its shared memory
+//    (the j side of the pair loop), recomputing the proposals redundantly - they cost O(N), the pair
+//    loop O(N^2/CL).
+//  * the pair loop is a packed single-precision SCREEN (box units, minimum image by the 1.5*2^23
+//    trick, add/sub/mul/fma.f32x2 on two j per instruction; see sweep_cached.cuh for the error bound
+//    that makes it a guaranteed superset) that collects a 32-bit hit mask per chunk of 32 j; the rare
+//    hits are then evaluated in double precision from the exact positions.  A pair outside the cutoff
+//    contributes exactly 0, so energies and forces are those of the all-FP64 loop, with the same
+//    j-ascending summation order; the FP64 pipe (1 warp instruction / 2 cycles on B200) is left to
+//    the pairs that matter.
+//  * the three MH sums are reduced per block, then across the cluster through distributed shared
+//    memory in rank order (deterministic); every block takes the same decision from the same
+//    Philox number.
+#pragma once
+#include <cooperative_groups.h>
+
+namespace smcb {
+namespace cg = cooperative_groups;
+
+struct StepSmem {
+    double *x, *y, *z;        // proposal positions, exact                    [3][Npad]
+    float *fx, *fy, *fz;      // the same in box units, screen precision      [3][Npad]
+    double *scratch;          // block_sum scratch                            [8*32]
+    double *part;             // this block's partial MH sums (read by the cluster peers) [4]
+    __device__ __forceinline__ void carve(double *base, int Npad)
+    {
+        x = base; y = x + Npad; z = y + Npad;
+        scratch = z + Npad;
+        part = scratch + 8 * 32;
+        fx = reinterpret_cast<float *>(part + 4); fy = fx + Npad; fz = fy + Npad;
+    }
+    static __host__ __device__ size_t bytes(int Npad)
+    {
+        return (size_t)(3 * Npad + 8 * 32 + 4) * sizeof(double) + (size_t)3 * Npad * sizeof(float);
+    }
+};
+
+// LJ energy (already *4), force and in-cutoff count of molecule i at (px,py,pz) against the staged
+// configuration; `self` is i's own index in that configuration (skipped)
+template <bool PZ>
+__device__ __forceinline__ void particle_vs_staged(const Box &b, const ScreenConsts &sc, const StepSmem &s, int N, int Npad,
+                                                   int self, double px, double py, double pz,
+                                                   double &e_lj, double &fx, double &fy, double &fz, unsigned &cnt)
+{
+    const float qx = (float)(px * b.invL), qy = (float)(py * b.invL), qz = (float)(pz * b.invL);
+    const float2 ax = make_float2(qx, qx), ay = make_float2(qy, qy), az = make_float2(qz, qz);
+    const float2 MG = make_float2(12582912.f, 12582912.f);
+    const float2 *X2 = reinterpret_cast<const float2 *>(s.fx), *Y2 = reinterpret_cast<const float2 *>(s.fy),
+                 *Z2 = reinterpret_cast<const float2 *>(s.fz);
+    double e = 0.0;
+    fx = fy = fz = 0.0;
+    for (int c0 = 0; c0 < Npad; c0 += 32) {
+        unsigned hits = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int j2 = (c0 >> 1) + k;
+            float2 sx = sub2(ax, X2[j2]);
+            sx = sub2(sx, sub2(add2(sx, MG), MG));
+            float2 sy = sub2(ay, Y2[j2]);
+            sy = sub2(sy, sub2(add2(sy, MG), MG));
+            float2 sz = sub2(az, Z2[j2]);
+            if (PZ) {
+                const float2 t = mul2(sz, make_float2(sc.inv_zper, sc.inv_zper));
+                sz = fma2(sub2(add2(t, MG), MG), make_float2(-sc.zper, -sc.zper), sz);
+            }
+            const float2 r2 = fma2(sz, sz, fma2(sy, sy, mul2(sx, sx)));
+            if (r2.x < sc.rc2s) hits |= 1u << (2 * k);
+            if (r2.y < sc.rc2s) hits |= 2u << (2 * k);
+        }
+        if ((self >> 5) == (c0 >> 5)) hits &= ~(1u << (self & 31));
+        while (hits) {                                   // rare in the gas; j ascending like the FP64 loop
+            const int j = c0 + __ffs(hits) - 1;
+            hits &= hits - 1;
+            double et, gx, gy, gz;
+            if (j < N && pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
+                e += et; fx += gx; fy += gy; fz += gz;
+                cnt++;
+            }
+        }
+    }
+    e_lj = 4.0 * e;
+}
+
+// one molecule against the surface, thread-serial: flat wall always (no cutoff, SMC.c:740-741), the M*M
+// sites only when the molecule is within the cutoff of the wall plane (none can be in range otherwise).
+// Returns the energy WITHOUT the final *4 and ADDS the force, like wall_particle.
+__device__ __forceinline__ double wall_point_fast(const Box &b, const double *__restrict__ W, double px, double py, double pz,
+                                                  double &fx, double &fy, double &fz)
+{
+    double e = 0.0;
+    const double dzw = wall_dz<false>(b, pz);
+    add_zwall(b, dzw, e, fz);
+    if (dzw * dzw < b.rc2) {
+        const double dw = b.L / b.M;
+        for (int i = 0; i < b.M; i++)
+            for (int j = 0; j < b.M; j++) {
+                const int m = j + i * b.M;
+                const double dx = min_image<false>(px - i * dw, b.L, b.invL);
+                const double dy = min_image<false>(py - j * dw, b.L, b.invL);
+                const double r2 = fma(dzw, dzw, fma(dy, dy, dx * dx));
+                if (r2 < b.rc2) {
+                    const double i2 = fast_rcp(r2);
+                    const double i6 = i2 * i2 * i2;
+                    const double a6 = W[2 * m] * i6;
+                    e += fma(a6, i6, -W[2 * m + 1] * i6);
+                    const double g = i2 * i6 * fma(48.0, a6, -24.0 * W[2 * m + 1]);
+                    fx = fma(g, dx, fx);
+                    fy = fma(g, dy, fy);
+                    fz = fma(g, dzw, fz);
+                }
+            }
+    }
+    return e;
+}
+
+// FED: host-fed noise (parity); PZ: bulk mode (z periodic); CL: blocks per chain (cluster size)
+template <bool FED, bool PZ, int CL>
+__device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const StepArgs &a)
+{
+    const int chain = blockIdx.x / CL, part = blockIdx.x % CL;
+    const int N = d.N, Npad = d.Npad, tid = threadIdx.x, T_ = blockDim.x;
+    extern __shared__ double sm[];
+    StepSmem s;
+    s.carve(sm, Npad);
+    __shared__ int s_accept;
+    const smcb_chain_params &cp = chain_params(d, chain);
+    const Box b = make_box(cp, d.M, d.step_scale);
+    const ScreenConsts sc = make_screen(b);
+    const double *W = d.W + (size_t)cp.wall * 2 * d.M * d.M;
+    double *P = d.pos + (size_t)chain * 3 * Npad;
+    double *Fc = a.F + (size_t)chain * 3 * Npad;
+    double *Fn = a.Fn + (size_t)chain * 3 * Npad;
+    double *DL = a.dl + (size_t)chain * 3 * Npad;
+
+    const double AoT = b.A / b.T;
+    const double sigma = sqrt(2.0 * b.A);
+    const RngId id{a.rng.k0, a.rng.k1, a.rng.chain0 + (uint32_t)chain};
+    unsigned cnt = 0;
+    double U = d.E[chain];
+    long long nacc = 0;
+
+    auto cluster_barrier = [&]() {
+        if (CL > 1) cg::this_cluster().sync();           // release/acquire at cluster scope: orders global and shared writes
+        else __syncthreads();
+    };
+    // stage one configuration: exact + box-unit single precision; pad slots far away
+    auto stage = [&](int j, double X, double Y, double Z) {
+        s.x[j] = X; s.y[j] = Y; s.z[j] = Z;
+        s.fx[j] = (float)(X * b.invL); s.fy[j] = (float)(Y * b.invL); s.fz[j] = (float)(Z * b.invL);
+    };
+    auto stage_pad = [&]() {
+        for (int j = N + tid; j < Npad; j += T_) { s.x[j] = 0.0; s.y[j] = 0.0; s.z[j] = 0.0; s.fx[j] = 0.f; s.fy[j] = 0.f; s.fz[j] = 3.0e18f; }
+    };
+    // forces / energies of this block's molecules at the staged configuration; returns the MH partial sums
+    auto evaluate_owned = [&](double *Fout, const double *Fold, bool with_mh, double (&t)[3]) {
+        t[0] = t[1] = t[2] = 0.0;
+        for (int i = part + CL * tid; i < N; i += CL * T_) {
+            const double px = s.x[i], py = s.y[i], pz = s.z[i];
+            double e_lj, fx, fy, fz;
+            particle_vs_staged<PZ>(b, sc, s, N, Npad, i, px, py, pz, e_lj, fx, fy, fz, cnt);
+            double e_wall = 0.0;
+            if (b.wall) {
+                double wx = 0.0, wy = 0.0, wz = 0.0;
+                e_wall = wall_point_fast(b, W, px, py, pz, wx, wy, wz) * 4;
+                fx += wx; fy += wy; fz += wz;
+            }
+            Fout[i] = fx; Fout[Npad + i] = fy; Fout[2 * Npad + i] = fz;
+            t[0] += 0.5 * e_lj + e_wall;
+            if (with_mh) {
+                const double ox = Fold[i], oy = Fold[Npad + i], oz = Fold[2 * Npad + i];
+                t[1] += DL[i] * (fx + ox) + DL[Npad + i] * (fy + oy) + DL[2 * Npad + i] * (fz + oz);
+                t[2] += (fx * fx - ox * ox) + (fy * fy - oy * oy) + (fz * fz - oz * oz);
+            }
+        }
+        block_sum<3>(t, s.scratch);
+        if (CL > 1) {                                     // cluster-wide sums through distributed shared memory, rank order
+            cg::cluster_group cl = cg::this_cluster();
+            if (tid == 0) { s.part[0] = t[0]; s.part[1] = t[1]; s.part[2] = t[2]; }
+            cl.sync();
+            double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+            for (int r = 0; r < CL; r++) {
+                const double *peer = cl.map_shared_rank(s.part, r);
+                r0 += peer[0]; r1 += peer[1]; r2 += peer[2];
+            }
+            cl.sync();                                    // peers are done reading before `part` is reused
+            t[0] = r0; t[1] = r1; t[2] = r2;
+        }
+    };
+
+    stage_pad();
+    if (a.refresh) {           // bring F and U in line with the positions
+        for (int j = tid; j < N; j += T_) stage(j, P[j], P[Npad + j], P[2 * Npad + j]);
+        __syncthreads();
+        double t[3];
+        evaluate_owned(Fc, Fc, false, t);
+        U = t[0];
+        cnt = 0;
+        cluster_barrier();     // every block's share of Fc is visible before the first proposal reads it
+    }
+
+    for (int st = 0; st < a.nsteps; st++) {
+        const unsigned long long step = a.rng.step0 + (unsigned long long)st;
+        const size_t sci = (size_t)st * d.C + chain;
+        // ---- proposal: d_j = F_j A/T + xi_j ; r' = wrap(r + d), all molecules, staged for the pair loop
+        for (int j = tid; j < N; j += T_) {
+            double g0, g1, g2;
+            if (FED) {
+                const double *xi = a.xi + sci * 3 * N;
+                g0 = xi[3 * j]; g1 = xi[3 * j + 1]; g2 = xi[3 * j + 2];
+            } else {
+                rng_particle_gauss(id, step, (uint32_t)j, g0, g1, g2);
+                g0 *= sigma; g1 *= sigma; g2 *= sigma;
+            }
+            const double dX = fma(Fc[j], AoT, g0), dY = fma(Fc[Npad + j], AoT, g1), dZ = fma(Fc[2 * Npad + j], AoT, g2);
+            if (j % CL == part) { DL[j] = dX; DL[Npad + j] = dY; DL[2 * Npad + j] = dZ; }      // owner keeps the displacement
+            double qx = P[j] + dX, qy = P[Npad + j] + dY, qz = P[2 * Npad + j] + dZ;
+            qx = min_image<false>(qx, b.L, b.invL);
+            qy = min_image<false>(qy, b.L, b.invL);
+            if (PZ) qz = min_image<false>(qz, b.Lz, b.invLz);
+            stage(j, qx, qy, qz);
+        }
+        __syncthreads();
+        // ---- forces and energy at the proposal, MH sums
+        double t[3];                       // U', sum d.(F'+F), sum |F'|^2-|F|^2
+        evaluate_owned(Fn, Fc, true, t);
+        const double lnap = -((t[0] - U) + t[1] / 2.0 + t[2] * b.A / (4.0 * b.T)) / b.T;
+        if (tid == 0) {
+            double uu;
+            if (FED) uu = a.u[sci];
+            else { uint32_t o; rng_step_scalars(id, step, o, uu); }
+            const int acc = uu < exp(lnap);
+            s_accept = acc;
+            if (part == 0) {
+                if (a.lnap) a.lnap[sci] = lnap;
+                if (a.accepted) a.accepted[sci] = (unsigned char)acc;
+            }
+        }
+        __syncthreads();
+        if (s_accept) {
+            for (int i = part + CL * tid; i < N; i += CL * T_) { P[i] = s.x[i]; P[Npad + i] = s.y[i]; P[2 * Npad + i] = s.z[i]; }
+            double *tp = Fc; Fc = Fn; Fn = tp;
+            U = t[0];
+            nacc++;
+        }
+        cluster_barrier();                 // positions / forces of this step are visible to the next proposal
+    }
+
+    double *Fcanon = a.F + (size_t)chain * 3 * Npad;
+    if (Fc != Fcanon)
+        for (int i = part + CL * tid; i < N; i += CL * T_) { Fcanon[i] = Fc[i]; Fcanon[Npad + i] = Fc[Npad + i]; Fcanon[2 * Npad + i] = Fc[2 * Npad + i]; }
+    double c[1] = {(double)cnt};
+    block_sum<1>(c, s.scratch);
+    if (tid == 0) {
+        if (part == 0) {
+            d.E[chain] = U;
+            d.nacc[chain] += nacc;
+            d.ntri[chain] += a.nsteps;
+            if (d.pair_counts) atomicAdd(d.pair_counts, (unsigned long long)a.nsteps * (unsigned long long)N * (N - 1));
+        }
+        if (d.pair_counts) atomicAdd(d.pair_counts + 1, (unsigned long long)c[0]);
+    }
+}
+
+template <bool FED, int CL>
+__global__ void __launch_bounds__(512) k_allparticle_fast(DevChains d, StepArgs a)
+{
+    if (chain_params(d, blockIdx.x / CL).flags & SMCB_PERIODIC_Z) allparticle_fast_body<FED, true, CL>(d, a);
+    else allparticle_fast_body<FED, false, CL>(d, a);
+}
+
+}  // namespace smcb

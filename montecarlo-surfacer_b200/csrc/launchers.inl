@@ -30,7 +30,7 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
     else     k_sweep<K, true, false><<<d.C, 32, smem, st>>>(d, a);
 #else
     const int MMpad = (d.M * d.M + 3) & ~3;
-    const size_t smem = ChainSmem::bytes(d.Npad, MMpad);
+    const size_t smem = ChainSmem::bytes(32 * K, MMpad);
     cudaError_t err;
     if (fed) {
         auto kern = k_sweep_cached<K, true>;
@@ -58,6 +58,56 @@ cudaError_t SMCB_CAT(launch_sweep_, SMCB_TU_SUFFIX)(bool fed, const DevChains &d
     return cudaErrorInvalidValue;
 }
 
+#if !SMCB_TU_IS_STRICT
+// blocks per chain of the FAST all-particle kernel: 1, or a thread-block cluster when a batch of few
+// large chains would leave SMs idle (config 5: 32 chains x N = 4096 per GPU -> clusters of 4)
+static int allparticle_cluster(const DevChains &d)
+{
+    if (const char *env = getenv("SMCB_CLUSTER")) {
+        const int v = atoi(env);
+        if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+    }
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int cl = 1;
+    while (cl < 8 && d.C * cl * 2 <= sms && d.N / (cl * 2) >= 256) cl *= 2;
+    return cl;
+}
+
+template <bool FED, int CL>
+static cudaError_t allparticle_fast_k(const DevChains &d, const StepArgs &a, cudaStream_t st)
+{
+    const size_t smem = StepSmem::bytes(d.Npad);
+    auto kern = k_allparticle_fast<FED, CL>;
+    cudaError_t err;
+    if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    int per = (d.N + CL - 1) / CL;
+    int threads = ((per + 31) / 32) * 32;
+    threads = threads > 512 ? 512 : (threads < 64 ? 64 : threads);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)d.C * CL);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, d, a);
+}
+
+cudaError_t launch_allparticle_fast(bool fed, const DevChains &d, const StepArgs &a, cudaStream_t st)
+{
+    switch (allparticle_cluster(d)) {
+    case 8: return fed ? allparticle_fast_k<true, 8>(d, a, st) : allparticle_fast_k<false, 8>(d, a, st);
+    case 4: return fed ? allparticle_fast_k<true, 4>(d, a, st) : allparticle_fast_k<false, 4>(d, a, st);
+    case 2: return fed ? allparticle_fast_k<true, 2>(d, a, st) : allparticle_fast_k<false, 2>(d, a, st);
+    default: return fed ? allparticle_fast_k<true, 1>(d, a, st) : allparticle_fast_k<false, 1>(d, a, st);
+    }
+}
+#else
 cudaError_t SMCB_CAT(launch_allparticle_, SMCB_TU_SUFFIX)(bool fed, const DevChains &d, const StepArgs &a, cudaStream_t st)
 {
     const size_t smem = (size_t)(6 * d.Npad + 8 * 32) * sizeof(double);
@@ -73,5 +123,6 @@ cudaError_t SMCB_CAT(launch_allparticle_, SMCB_TU_SUFFIX)(bool fed, const DevCha
     }
     return cudaGetLastError();
 }
+#endif
 
 }  // namespace smcb

@@ -36,17 +36,19 @@ struct ChainSmem {
     unsigned short *nb;       // cached number of LJ partners inside the cutoff
     double *site;             // [4][MMpad]: site x, y, a, b
     float *stage;             // [3][32]: speculative proposals of the slot being visited, in box units (screen precision)
-    __device__ __forceinline__ void carve(double *base, int Npad, int MMpad)
+    // NS = 32*K is a compile-time constant of the kernel instance, so every array but `site` sits at a
+    // constant offset from one base register
+    __device__ __forceinline__ void carve(double *base, int NS, int MMpad)
     {
-        x = base; y = x + Npad; z = y + Npad;
-        ce = z + Npad; cfx = ce + Npad; cfy = cfx + Npad; cfz = cfy + Npad;
-        site = cfz + Npad;
-        stage = reinterpret_cast<float *>(site + 4 * MMpad);
+        x = base; y = x + NS; z = y + NS;
+        ce = z + NS; cfx = ce + NS; cfy = cfx + NS; cfz = cfy + NS;
+        stage = reinterpret_cast<float *>(cfz + NS);
         nb = reinterpret_cast<unsigned short *>(stage + 3 * 32);
+        site = reinterpret_cast<double *>(nb + NS);       // NS is a multiple of 32: 8-byte aligned
     }
-    static __host__ __device__ size_t bytes(int Npad, int MMpad)
+    static __host__ __device__ size_t bytes(int NS, int MMpad)
     {
-        return (size_t)(7 * Npad + 4 * MMpad) * sizeof(double) + (size_t)(3 * 32) * sizeof(float) + (size_t)Npad * sizeof(unsigned short);
+        return (size_t)(7 * NS + 4 * MMpad) * sizeof(double) + (size_t)(3 * 32) * sizeof(float) + (size_t)NS * sizeof(unsigned short);
     }
 };
 
@@ -250,7 +252,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
     const int MM = d.M * d.M, MMpad = (MM + 3) & ~3;
     extern __shared__ double sm[];
     ChainSmem s;
-    s.carve(sm, Npad, MMpad);
+    s.carve(sm, 32 * K, MMpad);
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, d.step_scale);
     const double *W = d.W + (size_t)cp.wall * 2 * MM;
