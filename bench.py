@@ -49,10 +49,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="smcb200", choices=["smcb200", "reference"])
-    ap.add_argument("--chains", type=int, default=8192, help="chains per GPU")
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default 8192; largeN: 256/world)")
     ap.add_argument("--sweeps-per-step", type=int, default=40)
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--kernel", default="sweep", choices=["sweep", "allparticle"])
+    ap.add_argument("--workload", default="batched", choices=["batched", "largeN"],
+                    help="batched: 8192 chains x N=256 per GPU (configs[2], the headline); largeN: 256 chains x N=4096 in "
+                         "total, sharded over the GPUs (configs[4], all-particle kernel with thread-block clusters)")
+    ap.add_argument("--thermalise", type=int, default=2000,
+                    help="sweeps with 2A (sMC's thermalisation, SMC.c:110-125) before the extra 'thermalised' timing leg; 0 = skip")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -222,13 +227,20 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    Cn, N, S = args.chains, N_PART, args.sweeps_per_step
+    Cn, N, S = args.chains or 8192, N_PART, args.sweeps_per_step
+    total_largeN = 256
+    if args.workload == "largeN":                   # configs[4]: 256 chains x N=4096 in total, strong-sharded
+        N, args.kernel = 4096, "allparticle"
+        Cn = args.chains or smcb.shard_chains(256, world, rank).nchains      # --chains 32 emulates one rank of 8
+        total_largeN = float(world) * Cn if args.chains else 256.0
     mode = smcb.STRICT if args.mode == "strict" else smcb.FAST
-    A = TEMP if args.kernel == "sweep" else 2e-4
+    A = TEMP if args.kernel == "sweep" else (2e-4 if N <= 256 else 2e-6)
 
     # start lattice of initializeBox(33, 240, 256) (SMC.c:413-465): 4x4x4 fcc cells, a = 8.25, shifted a/4
-    a = L_BOX / 4
-    cells = np.array([(i, j, k) for i in range(4) for j in range(4) for k in range(4)], dtype=float)
+    # (N=4096: 16x16x4 cells, a = 33/16 - the reference's own generator is invalid there)
+    nxy, nz = (4, 4) if N == 256 else (16, 4)
+    a = L_BOX / nxy
+    cells = np.array([(i, j, k) for i in range(nxy) for j in range(nxy) for k in range(nz)], dtype=float)
     basis = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]])
     X = (cells[:, None, :] + basis[None, :, :]).reshape(-1, 3) * a + a / 4
     Pz = LZ_BOX - LZ_BOX / 20.0
@@ -248,8 +260,8 @@ def main():
     obs_mom = torch.zeros(lay.f64_total, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
-    def run_kernel():
-        if args.kernel == "sweep":
+    def run_kernel(kernel):
+        if kernel == "sweep":
             eng.sweep(S, mode)
         else:
             eng.step_allparticle(S, mode)
@@ -262,15 +274,14 @@ def main():
         eng.obs_export_device(obs_cnt.data_ptr(), obs_mom.data_ptr())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.all_reduce(obs_cnt)
-        dist.all_reduce(obs_mom)
+        smcb.allreduce_observables(obs_cnt, obs_mom)
         e1.record()
         torch.cuda.synchronize()
         eng.obs_reset()          # ranks keep accumulating deltas; the reduced block lives in obs_cnt/obs_mom
         return e0.elapsed_time(e1)
 
-    def one_step():
-        k_ms = run_kernel()
+    def one_step(kernel):
+        k_ms = run_kernel(kernel)
         pairs = eng.last_pair_counts()
         eng.gather()
         g_ms = eng.last_kernel_ms()[0]
@@ -283,36 +294,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_leg(kernel, nsteps, warmup, sample_clocks=False):
+        """`warmup` untimed steps, then exactly `nsteps` steps between barriers; device times (CUDA events
+        on the engine's stream) summed per rank, max over ranks"""
+        for _ in range(warmup):
+            one_step(kernel)
+        sampler = ClockSampler(local) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        t0 = time.perf_counter()
+        k_tot = g_tot = c_tot = 0.0
+        pairs_tot = pairs_cut = 0
+        eng.reset_counters()
+        for _ in range(nsteps):
+            flush.fill_(1)                      # L2 flush between timed iterations (untimed)
+            torch.cuda.synchronize()
+            k_ms, g_ms, c_ms, pairs = one_step(kernel)
+            k_tot += k_ms; g_tot += g_ms; c_tot += c_ms
+            pairs_tot += pairs[0]; pairs_cut += pairs[1]
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        _, na, nt = eng.chain_state()
+        dev_ms = smcb.max_over_ranks(k_tot + g_tot + c_tot, device="cuda")
+        k_max = smcb.max_over_ranks(k_tot, device="cuda")
+        unit_pairs = pairs_per_sweep(N) if kernel == "sweep" else float(N) * (N - 1)
+        total_chains = float(world) * Cn if args.workload == "batched" else total_largeN
+        chain_steps = total_chains * S * nsteps
+        flops = FLOPS_PAIR * pairs_tot + FLOPS_INCUT * pairs_cut
+        return {"value": chain_steps * unit_pairs / (dev_ms * 1e-3), "chain_steps_per_s": chain_steps / (dev_ms * 1e-3),
+                "ms_per_step": dev_ms / nsteps, "kernel_ms_per_step": k_max / nsteps, "gather_ms_per_step": g_tot / nsteps,
+                "allreduce_ms_per_step": c_tot / nsteps, "wall_s": wall, "clocks": clocks,
+                "pairs_in_cutoff_frac": pairs_cut / max(1, pairs_tot), "acceptance": float(na.sum()) / max(1, int(nt.sum())),
+                "achieved_tflops": flops / (k_tot * 1e-3) / 1e12, "unit_pairs": unit_pairs}
+
     fp64_peak, _ = eng.measure_fp64_peak()
-
-    for _ in range(max(args.warmup, 3)):
-        one_step()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    t_wall0 = time.perf_counter()
-    k_tot = g_tot = c_tot = 0.0
-    pairs_tot = pairs_cut = 0
-    for _ in range(args.steps):
-        flush.fill_(1)                      # L2 flush between timed iterations (untimed)
-        torch.cuda.synchronize()
-        k_ms, g_ms, c_ms, pairs = one_step()
-        k_tot += k_ms; g_tot += g_ms; c_tot += c_ms
-        pairs_tot += pairs[0]; pairs_cut += pairs[1]
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-
-    dev_ms = k_tot + g_tot + c_tot
-    if dist is not None:
-        t = torch.tensor([dev_ms, k_tot], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, k_max = t.tolist()
-    else:
-        k_max = k_tot
-    unit_pairs = pairs_per_sweep(N) if args.kernel == "sweep" else float(N) * (N - 1)
-    chain_steps = float(world) * Cn * S * args.steps
-    value = chain_steps * unit_pairs / (dev_ms * 1e-3)
+    W = max(args.warmup, 3)
+    main = timed_leg(args.kernel, args.steps, W, sample_clocks=True)
 
     # ---- end to end through the C-ABI with host buffers (every rank, max over ranks) ----------
     e2e = None
@@ -323,7 +342,7 @@ def main():
 
         def e2e_step():
             eng.set_positions(host_R)                  # H2D of the step's inputs
-            run_kernel()
+            run_kernel(args.kernel)
             eng.gather()
             allreduce_obs()
             eng.get_positions(host_R)                  # D2H of the step's results
@@ -335,43 +354,74 @@ def main():
         for _ in range(nsteps_e2e):
             e2e_step()
         barrier()
-        te = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([te], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            te = t.item()
-        e2e = {"value": float(world) * Cn * S * nsteps_e2e * unit_pairs / te, "unit": "pair-interactions/s",
-               "chain_steps_per_s": float(world) * Cn * S * nsteps_e2e / te, "steps": nsteps_e2e,
+        te = smcb.max_over_ranks(time.perf_counter() - t0, device="cuda")
+        total_chains = float(world) * Cn if args.workload == "batched" else total_largeN
+        e2e = {"value": total_chains * S * nsteps_e2e * main["unit_pairs"] / te, "unit": "pair-interactions/s",
+               "chain_steps_per_s": total_chains * S * nsteps_e2e / te, "steps": nsteps_e2e,
                "h2d_bytes_per_step": int(Cn * 3 * N * 8), "d2h_bytes_per_step": int(Cn * 3 * N * 8 + Cn * 24),
                "timing": "host wall clock around set_positions -> kernel -> gather -> get_positions -> chain_state"}
 
+    # ---- extra legs (reported beside the headline, same JSON line) -----------------------------
+    extra = {}
+    if args.workload == "batched" and args.kernel == "sweep" and mode == smcb.FAST:
+        if args.thermalise > 0:
+            # sMC's thermalisation (2A, SMC.c:110-125) so molecules reach the wall and partners become common
+            eng.set_step_scale(2.0)
+            eng.sweep(args.thermalise, mode)
+            eng.set_step_scale(1.0)
+            th = timed_leg("sweep", max(2, min(args.steps, 3)), 1)
+            extra["thermalised"] = {k: th[k] for k in ("value", "chain_steps_per_s", "ms_per_step", "kernel_ms_per_step",
+                                                       "pairs_in_cutoff_frac", "acceptance")}
+            extra["thermalised"].update(sweeps_before=args.thermalise, roofline_frac=th["achieved_tflops"] / fp64_peak)
+        # north-star kernel B on the same chains: all-particle steps need a small A to be accepted at all
+        eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=2e-4), GOLDEN_W_M3, ngroups=1)
+        eng.obs_configure(nebins=64, e_lo=-8.0, e_hi=2.0)
+        eng.broadcast_positions(R0)
+        ap_ = timed_leg("allparticle", max(2, min(args.steps, 3)), 2)
+        extra["allparticle_kernel"] = {k: ap_[k] for k in ("value", "chain_steps_per_s", "ms_per_step", "kernel_ms_per_step",
+                                                            "pairs_in_cutoff_frac", "acceptance")}
+        extra["allparticle_kernel"].update(A=2e-4, roofline_frac=ap_["achieved_tflops"] / fp64_peak,
+                                           note="one all-particle Smart-MC step = N(N-1) ordered pair-interactions")
+
     if rank == 0:
-        flops = FLOPS_PAIR * pairs_tot + FLOPS_INCUT * pairs_cut
-        achieved = flops / (k_tot * 1e-3) / 1e12
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath)).get(args.kernel)
+            if tj:
+                traffic = tj["dram_bytes_per_chain_launch"] * Cn
+                traffic_note = tj["source"]
         line = {
-            "metric": "pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
-            "chain_steps_per_s": chain_steps / (dev_ms * 1e-3),
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "pair_interactions_per_s", "value": main["value"], "unit": "pair-interactions/s",
+            "chain_steps_per_s": main["chain_steps_per_s"],
+            "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak" if args.workload == "batched" else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{Cn} chains/GPU x N={N} with wall (BASELINE configs[2]), {args.kernel} kernel, {args.mode}",
+            "config": {"workload": (f"{Cn} chains/GPU x N={N} with wall (BASELINE configs[2])" if args.workload == "batched"
+                                    else f"{int(total_largeN)} chains x N={N} with wall in total (BASELINE configs[4]), {Cn} on this rank")
+                                   + f", {args.kernel} kernel, {args.mode}",
                        "chains_per_gpu": Cn, "N": N, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": A,
                        "sweeps_per_step": S, "start": "initializeBox fcc lattice + warm-up steps",
                        "l2": "flushed between timed steps (256 MB write)", "rng": "Philox4x32-10",
                        "parallelism": f"chains sharded x{world}, NCCL all-reduce of the observable block only"},
-            "kernel_ms_per_step": k_max / args.steps, "gather_ms_per_step": g_tot / args.steps,
-            "allreduce_ms_per_step": c_tot / args.steps, "wall_s_timed_region": t_wall,
-            "pairs_in_cutoff_frac": pairs_cut / max(1, pairs_tot),
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
-                         "note": "algorithmic flops = 17/ordered pair + 16 more inside the cutoff (SURVEY §8d); peak = DFMA "
-                                 "peak measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); FP64-pipe "
-                                 "utilisation from ncu is in profiles/"},
-            "clocks": clocks, "gpu_launches": args.steps * 3, "device": info,
+            "kernel_ms_per_step": main["kernel_ms_per_step"], "gather_ms_per_step": main["gather_ms_per_step"],
+            "allreduce_ms_per_step": main["allreduce_ms_per_step"], "wall_s_timed_region": main["wall_s"],
+            "pairs_in_cutoff_frac": main["pairs_in_cutoff_frac"], "acceptance": main["acceptance"],
+            "roofline": {"bound": "fp64", "achieved": main["achieved_tflops"], "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": main["achieved_tflops"] / fp64_peak, "traffic": traffic, "traffic_note": traffic_note,
+                         "note": "ALGORITHMIC flops = 17 per ordered pair-interaction + 16 more inside the cutoff (SURVEY §8d), "
+                                 "a sweep counted as the reference executes it: 2N(N-1) pair-interactions (old + proposed "
+                                 "position of every trial).  The kernel evaluates fewer: old-position terms are cached, and the "
+                                 "cutoff screen runs in packed FP32 (exact FP64 for the pairs inside), so frac is a figure of "
+                                 "merit against the FP64 peak, not FP64-pipe utilisation - that is in profiles/ (ncu).  peak = "
+                                 "DFMA peak measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"},
+            "clocks": main["clocks"], "gpu_launches": args.steps * 3, "device": info,
         }
+        line.update(extra)
         if e2e:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and N == N_PART:
             cb = cpu_baseline(args)
             if cb:
                 line["cpu_baseline"] = cb

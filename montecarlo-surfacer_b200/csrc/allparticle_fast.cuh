@@ -48,17 +48,18 @@ struct StepSmem {
 
 // LJ energy (already *4), force and in-cutoff count of molecule i at (px,py,pz) against the staged
 // configuration; `self` is i's own index in that configuration (skipped)
-template <bool PZ>
+template <bool PZ, bool VIR = false>
 __device__ __forceinline__ void particle_vs_staged(const Box &b, const ScreenConsts &sc, const StepSmem &s, int N, int Npad,
                                                    int self, double px, double py, double pz,
-                                                   double &e_lj, double &fx, double &fy, double &fz, unsigned &cnt)
+                                                   double &e_lj, double &fx, double &fy, double &fz, unsigned &cnt,
+                                                   double *vir = nullptr)
 {
     const float qx = (float)(px * b.invL), qy = (float)(py * b.invL), qz = (float)(pz * b.invL);
     const float2 ax = make_float2(qx, qx), ay = make_float2(qy, qy), az = make_float2(qz, qz);
     const float2 MG = make_float2(12582912.f, 12582912.f);
     const float2 *X2 = reinterpret_cast<const float2 *>(s.fx), *Y2 = reinterpret_cast<const float2 *>(s.fy),
                  *Z2 = reinterpret_cast<const float2 *>(s.fz);
-    double e = 0.0;
+    double e = 0.0, v = 0.0;
     fx = fy = fz = 0.0;
     for (int c0 = 0; c0 < Npad; c0 += 32) {
         unsigned hits = 0;
@@ -86,10 +87,15 @@ __device__ __forceinline__ void particle_vs_staged(const Box &b, const ScreenCon
             if (j < N && pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
                 e += et; fx += gx; fy += gy; fz += gz;
                 cnt++;
+                if (VIR) {                               // pressure()'s pair term 24/r^6 - 48/r^12 (SMC.c:712-714)
+                    double dx, dy, dz;
+                    v += virial_term<false>(pair_sep<false>(b, px, py, pz, s.x[j], s.y[j], s.z[j], dx, dy, dz));
+                }
             }
         }
     }
     e_lj = 4.0 * e;
+    if (VIR) *vir = v;
 }
 
 // one molecule against the surface, thread-serial: flat wall always (no cutoff, SMC.c:740-741), the M*M
@@ -271,6 +277,86 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
         if (d.pair_counts) atomicAdd(d.pair_counts + 1, (unsigned long long)c[0]);
     }
 }
+
+// ---- FAST static evaluation (rows a2-a10 of the survey) with the same screened pair loop ----------------
+// `parts` blocks per chain (plain grid, no cluster): block `part` owns molecules part, part+parts, ...; every
+// block stages the whole chain.  Chain totals: each block leaves its partial sums in `partials`, and the LAST
+// block of a chain to finish (atomic ticket) adds them in part order, so the totals do not depend on scheduling.
+struct EvalFastArgs {
+    int parts;
+    double *partials;          // [C][parts][4]
+    unsigned *tickets;         // [C], zeroed by the launcher's caller, left zero again by the kernel
+};
+
+template <bool PZ>
+__device__ __forceinline__ void evaluate_fast_body(const DevChains &d, const EvalOut &o, const EvalFastArgs &ea)
+{
+    const int parts = ea.parts, chain = blockIdx.x / parts, part = blockIdx.x % parts;
+    const int N = d.N, Npad = d.Npad, tid = threadIdx.x, T_ = blockDim.x;
+    extern __shared__ double sm[];
+    StepSmem s;
+    s.carve(sm, Npad);
+    __shared__ unsigned s_last;
+    const smcb_chain_params &cp = chain_params(d, chain);
+    const Box b = make_box(cp, d.M, 1.0);
+    const ScreenConsts sc = make_screen(b);
+    const double *W = d.W + (size_t)cp.wall * 2 * d.M * d.M;
+    const double *P = d.pos + (size_t)chain * 3 * Npad;
+    for (int j = tid; j < Npad; j += T_) {
+        const bool in = j < N;
+        const double X = in ? P[j] : 0.0, Y = in ? P[Npad + j] : 0.0, Z = in ? P[2 * Npad + j] : 0.0;
+        s.x[j] = X; s.y[j] = Y; s.z[j] = Z;
+        s.fx[j] = (float)(X * b.invL); s.fy[j] = (float)(Y * b.invL); s.fz[j] = in ? (float)(Z * b.invL) : 3.0e18f;
+    }
+    __syncthreads();
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    unsigned cnt = 0;
+    for (int i = part + parts * tid; i < N; i += parts * T_) {
+        const double px = s.x[i], py = s.y[i], pz = s.z[i];
+        double e_lj, fx, fy, fz, vir;
+        particle_vs_staged<PZ, true>(b, sc, s, N, Npad, i, px, py, pz, e_lj, fx, fy, fz, cnt, &vir);
+        double e_wall = 0.0, wx = 0.0, wy = 0.0, wz = 0.0;
+        if (b.wall) {
+            e_wall = wall_point_fast(b, W, px, py, pz, wx, wy, wz) * 4;
+            tot[3] += wall_virial_ref<false>(b, W, px, py, pz);
+        }
+        const size_t q = (size_t)chain * Npad + i, q3 = (size_t)chain * 3 * Npad + i;
+        if (o.e_lj) o.e_lj[q] = e_lj;
+        if (o.e_wall) o.e_wall[q] = e_wall;
+        if (o.f_lj) { o.f_lj[q3] = fx; o.f_lj[q3 + Npad] = fy; o.f_lj[q3 + 2 * Npad] = fz; }
+        if (o.f_wall) { o.f_wall[q3] = wx; o.f_wall[q3 + Npad] = wy; o.f_wall[q3 + 2 * Npad] = wz; }
+        tot[0] += 0.5 * e_lj;
+        tot[1] += e_wall;
+        tot[2] += 0.5 * vir;
+    }
+    block_sum<4>(tot, s.scratch);
+    if (!o.totals) return;
+    double *mine = ea.partials + ((size_t)chain * parts + part) * 4;
+    if (tid == 0) {
+        mine[0] = tot[0]; mine[1] = tot[1]; mine[2] = tot[2]; mine[3] = tot[3];
+        __threadfence();
+        s_last = atomicAdd(ea.tickets + chain, 1u) == (unsigned)(parts - 1);
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        const double *pp = ea.partials + (size_t)chain * parts * 4;
+        double r[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int p = 0; p < parts; p++)
+            for (int k = 0; k < 4; k++) r[k] += pp[4 * p + k];
+        double *t = o.totals + (size_t)chain * 4;
+        t[0] = r[0]; t[1] = r[1]; t[2] = r[2]; t[3] = r[3];
+        ea.tickets[chain] = 0;
+    }
+}
+
+#ifdef SMCB_MISC_KERNELS      // not a template: compiled once, in kernels_fast.cu
+__global__ void __launch_bounds__(512) k_evaluate_fast(DevChains d, EvalOut o, EvalFastArgs ea)
+{
+    if (chain_params(d, blockIdx.x / ea.parts).flags & SMCB_PERIODIC_Z) evaluate_fast_body<true>(d, o, ea);
+    else evaluate_fast_body<false>(d, o, ea);
+}
+#endif
 
 template <bool FED, int CL>
 __global__ void __launch_bounds__(512) k_allparticle_fast(DevChains d, StepArgs a)

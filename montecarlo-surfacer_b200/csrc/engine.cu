@@ -65,6 +65,8 @@ struct smcb_engine {
     DevBuf<unsigned long long> pairs, counters;
     DevBuf<unsigned char> fed_acc;
     DevBuf<int> rbin, trace_acc;
+    DevBuf<double> eval_partials;
+    DevBuf<unsigned> eval_tickets;
     DevBuf<double> trace_E;
     uint64_t seed = 0x5eed5eedull, step = 0;
     uint32_t chain0 = 0;
@@ -158,7 +160,7 @@ int smcb_destroy(smcb_engine *e)
     e->F.release(); e->Fn.release(); e->dl.release(); e->e_lj.release(); e->f_lj.release();
     e->e_wall.release(); e->f_wall.release(); e->totals.release(); e->moments.release();
     e->peak_out.release(); e->fed_a.release(); e->fed_b.release(); e->nacc.release(); e->ntri.release();
-    e->cache_out.release(); e->trace_E.release(); e->trace_acc.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
+    e->cache_out.release(); e->eval_partials.release(); e->eval_tickets.release(); e->trace_E.release(); e->trace_acc.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -290,7 +292,18 @@ static int run_evaluate(smcb_engine *e, int mode, const EvalOut &o)
     DevChains d = e->chains();
     d.step_scale = 1.0;
     d.pair_counts = nullptr;
-    CK(mode == SMCB_STRICT ? launch_evaluate_strict(d, o, e->stream) : launch_evaluate_fast(d, o, e->stream));
+    if (mode == SMCB_STRICT) {
+        CK(launch_evaluate_strict(d, o, e->stream));
+        return SMCB_OK;
+    }
+    // FAST: packed-FP32 screened pair loop, several blocks per chain when the batch is small
+    const int parts = evaluate_fast_parts(d);
+    CK(e->eval_partials.ensure((size_t)e->C * parts * 4));
+    if (e->eval_tickets.n < (size_t)e->C) {
+        CK(e->eval_tickets.ensure(e->C));
+        CK(cudaMemsetAsync(e->eval_tickets.p, 0, e->C * sizeof(unsigned), e->stream));
+    }
+    CK(launch_evaluate_fast_screened(d, o, parts, e->eval_partials.p, e->eval_tickets.p, e->stream));
     return SMCB_OK;
 }
 

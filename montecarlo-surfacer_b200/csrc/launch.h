@@ -14,6 +14,8 @@ namespace smcb {
 SMCB_DECLARE_LAUNCHERS(fast)
 SMCB_DECLARE_LAUNCHERS(strict)
 
+int evaluate_fast_parts(const DevChains &d);
+cudaError_t launch_evaluate_fast_screened(const DevChains &d, const EvalOut &o, int parts, double *partials, unsigned *tickets, cudaStream_t st);
 cudaError_t launch_gather(const DevChains &d, const GatherArgs &g, cudaStream_t st);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, int C, int N, int Npad, int ncomp, cudaStream_t st);
 cudaError_t launch_soa_to_aos(const double *soa, double *aos, int C, int N, int Npad, int ncomp, cudaStream_t st);

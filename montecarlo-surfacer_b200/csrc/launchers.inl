@@ -8,8 +8,33 @@ namespace smcb {
 static inline int eval_threads(int N)
 {
     int t = ((N + 31) / 32) * 32;
-    return t > 1024 ? 1024 : (t < 64 ? 64 : t);
+    return t > 512 ? 512 : (t < 64 ? 64 : t);     // 100-120 registers per thread: 512 is the largest block that launches
 }
+
+#if !SMCB_TU_IS_STRICT
+// blocks per chain of the FAST evaluation: enough to put at least ~2 blocks on every SM
+int evaluate_fast_parts(const DevChains &d)
+{
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int parts = 1;
+    while (parts < 16 && d.C * parts < 2 * sms && d.N / (parts * 2) >= 128) parts *= 2;
+    return parts;
+}
+
+cudaError_t launch_evaluate_fast_screened(const DevChains &d, const EvalOut &o, int parts, double *partials, unsigned *tickets, cudaStream_t st)
+{
+    const size_t smem = StepSmem::bytes(d.Npad);
+    cudaError_t err = cudaFuncSetAttribute(k_evaluate_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int per = (d.N + parts - 1) / parts;
+    int threads = ((per + 31) / 32) * 32;
+    threads = threads > 512 ? 512 : (threads < 64 ? 64 : threads);
+    EvalFastArgs ea{parts, partials, tickets};
+    k_evaluate_fast<<<d.C * parts, threads, smem, st>>>(d, o, ea);
+    return cudaGetLastError();
+}
+#endif
 
 cudaError_t SMCB_CAT(launch_evaluate_, SMCB_TU_SUFFIX)(const DevChains &d, const EvalOut &o, cudaStream_t st)
 {

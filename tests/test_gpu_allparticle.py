@@ -108,3 +108,60 @@ def test_allparticle_philox_energy_bookkeeping(orc):
     assert np.all(nt == 80) and na.sum() > 0
     Erec = ev["U_lj"] + ev["U_wall"]
     assert np.all(np.abs(E - Erec) <= 1e-10 * np.maximum(1.0, np.abs(Erec)))
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+def test_allparticle_large_N_cluster_matches_oracle(orc, cluster, monkeypatch):
+    """N = 1024 with the chain split over a thread-block cluster (DSMEM reduction of the MH sums):
+    every cluster size must reproduce the oracle's step (ln ap within 1e-9, same decisions)"""
+    from oracle_bindings import config_droplet, config_gas
+    monkeypatch.setenv("SMCB_CLUSTER", str(cluster))
+    N, M, T, A, nsteps = 1024, 3, 1.1, 2e-5, 5
+    L, Lz = 33.0, 240.0
+    s = make_sys(N, M, L, Lz)
+    W = GOLDEN_W_M3.copy()
+    rng = np.random.default_rng(99)
+    R0 = np.stack([config_droplet(N, L, Lz, rng, jitter=0.04, nz=8), config_gas(N, L, Lz, rng)])
+    xi = rng.standard_normal((nsteps, 2, 3 * N)) * np.sqrt(2 * A)
+    u = rng.random((nsteps, 2))
+    with smcb.Engine(2, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
+        eng.set_positions(R0)
+        lnap, acc = eng.step_allparticle_fed(xi, u, mode=smcb.FAST)
+        R = eng.get_positions()
+        E, na, nt = eng.chain_state()
+    for c in range(2):
+        Ro = R0[c].copy()
+        F, Ulj, Uw, _ = orc.total(s, Ro, W)
+        U = Ulj + Uw
+        for k in range(nsteps):
+            ok, U, ln = orc.allparticle_step(s, Ro, F, U, W, A, T, xi[k, c], u[k, c])
+            assert abs(lnap[k, c] - ln) <= 1e-9 * max(1.0, abs(ln)), (k, c, lnap[k, c], ln)
+            assert bool(acc[k, c]) == bool(ok), (k, c)
+        assert rel_err(R[c], Ro) < 1e-11
+        assert abs(E[c] - U) <= 1e-10 * max(1.0, abs(U))
+
+
+def test_allparticle_N4096_config5_invariants(orc):
+    """BASELINE configs[4] shape (N = 4096 with wall; clusters picked automatically for a small batch):
+    the energy carried by the kernel equals a fresh evaluation, and a second call reuses the forces"""
+    N, M, T, A = 4096, 3, 1.1, 2e-6
+    L, Lz = 33.0, 240.0
+    W = GOLDEN_W_M3.copy()
+    X = orc.fcc_lattice(L, Lz, 16, 16, 4)                   # the corrected N=4096 lattice (SURVEY §7)
+    assert X.size == 3 * N
+    rng = np.random.default_rng(3)
+    R0 = np.stack([X + 0.02 * rng.standard_normal(3 * N) for _ in range(4)])
+    with smcb.Engine(4, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
+        eng.set_positions(R0)
+        eng.set_rng(11, 0, 0)
+        eng.step_allparticle(6, smcb.FAST)
+        eng.step_allparticle(6, smcb.FAST)
+        E, na, nt = eng.chain_state()
+        ev = eng.evaluate(smcb.FAST, per_particle=False)
+        tot, cut = eng.last_pair_counts()
+    assert np.all(nt == 12) and na.sum() > 0
+    assert tot == 4 * 6 * N * (N - 1) and cut > 0
+    Erec = ev["U_lj"] + ev["U_wall"]
+    assert np.all(np.abs(E - Erec) <= 1e-10 * np.maximum(1.0, np.abs(Erec)))
