@@ -212,6 +212,9 @@ def main():
         reference_arm(args)
         return
 
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     smcb = importlib.import_module("montecarlo-surfacer_b200")
     from oracle_bindings import GOLDEN_W_M3
@@ -425,7 +428,7 @@ def main():
             cb = cpu_baseline(args)
             if cb:
                 line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -344,17 +344,20 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
             if (tb < te) {
                 // Each lane prepares its own particle of this slot (lane <-> particle 32*slot+lane): the random
                 // inputs, and SPECULATIVELY the whole trial under the assumption that nobody is in range of the
-                // proposal - proposal from the cached force, flat-wall terms there, acceptance.  That is the
-                // common case in the gas phase, and there a trial costs only the O(N) screen below.  The
-                // speculation of lane t is void ("slow") when its particle has partners at the old position,
-                // when the proposal comes within the cutoff of the surface, when the screen finds a partner, or
-                // when an earlier accepted trial of this segment touched its caches (dirty).
+                // proposal - proposal from the cached force, flat-wall terms there, acceptance.  Then the trials
+                // are resolved in visiting order, each on the cheapest path that is still exact:
+                //   fast    the screen finds nobody near the proposal: the speculated decision stands; if the move
+                //           is accepted and the OLD position had partners, they lose the pair terms (medium);
+                //   general partners at the proposal, or the proposal is within the cutoff of the surface, or an
+                //           earlier accepted trial of this segment touched this particle's caches (dirty):
+                //           energy/force at the proposal are summed over the warp; the speculated proposal and
+                //           flat-wall terms are reused unless the speculation is void (near / dirty).
                 const int nl = 32 * slot + lane;
                 const bool mine = lane >= tb && lane < te;
                 __syncwarp();                           // the previous segment is done with the staging area
                 double g0 = 0.0, g1 = 0.0, g2 = 0.0, lul = 0.0;
-                double p_qx = 0.0, p_qy = 0.0, p_qz = 0.0, p_Un = 0.0, p_fz = 0.0, p_dU = 0.0;
-                bool p_slow = false, p_acc = false;
+                double p_qx = 0.0, p_qy = 0.0, p_qz = 0.0, p_ew = 0.0, p_fz = 0.0, p_dU = 0.0;
+                bool p_near = false, p_acc = false;
                 if (mine) {
                     double ul;
                     if (FED) {
@@ -375,40 +378,67 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                     p_qy = min_image<false>(s.y[nl] + dY, b.L, b.invL);
                     p_qz = s.z[nl] + dZ;
                     if (PZ) p_qz = min_image<false>(p_qz, b.Lz, b.invLz);
-                    double ew = 0.0;
-                    bool near = false;
                     if (b.wall) {
                         const double dzw = wall_dz<false>(b, p_qz);
-                        near = dzw * dzw < b.rc2;
-                        add_zwall(b, dzw, ew, p_fz);
+                        p_near = dzw * dzw < b.rc2;
+                        add_zwall(b, dzw, p_ew, p_fz);
                     }
-                    p_Un = 4.0 * ew;                                                                      // SMC.c:319, no partners
+                    const double Un0 = 4.0 * p_ew;                                                        // SMC.c:319, no partners
                     const double f2 = p_fz * p_fz - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
                     const double dr = fma(dX, Fmx, fma(dY, Fmy, dZ * (p_fz + Fmz)));
-                    p_dU = p_Un - Um;
+                    p_dU = Un0 - Um;
                     const double xarg = -(p_dU + 0.5 * dr + f2 * quarterAoT) * invT;                      // SMC.c:326-329
                     p_acc = (lul < xarg) && (xarg > -745.1332191019411);
-                    p_slow = near || s.nb[nl] != 0;
                     s.stage[lane] = (float)(p_qx * b.invL); s.stage[32 + lane] = (float)(p_qy * b.invL); s.stage[64 + lane] = (float)(p_qz * b.invL);
                 }
                 __syncwarp();
-                const unsigned slow0 = __ballot_sync(FULL, p_slow);
+                const unsigned near0 = __ballot_sync(FULL, p_near);
                 const unsigned acc0 = __ballot_sync(FULL, p_acc);
                 unsigned dirty = 0;
+                // the partners of particle m's CURRENT (old) position lose their pair terms with m (force on j from m = -g d);
+                // returns whether a particle of the slot being visited (physical slot 0) was touched
+                auto drop_old_partners = [&](int m, unsigned okm) -> bool {
+                    const double px = s.x[m], py = s.y[m], pz = s.z[m];
+                    unsigned ho = screen_slots<K, PZ>(sc, (float)(px * b.invL), (float)(py * b.invL), (float)(pz * b.invL), q) & okm;
+                    bool touched = false;
+                    while (ho) {
+                        const int k = __ffs(ho) - 1;
+                        ho &= ho - 1;
+                        const int j = particle_of(k);
+                        double et, hx, hy, hz;
+                        if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
+                            s.ce[j] -= 4.0 * et; s.cfx[j] += hx; s.cfy[j] += hy; s.cfz[j] += hz;
+                            s.nb[j] -= 1;
+                            touched |= (k == 0);
+                        }
+                    }
+                    return touched;
+                };
                 for (int t = tb; t < te; t++) {
                     const int n = 32 * slot + t;
                     const unsigned okmask = validmask & ~((lane == t) ? 1u : 0u);
-                    if (!(((slow0 | dirty) >> t) & 1u)) {
-                        // ---- speculative path: one screen of the lane's K slots against the staged proposal
-                        const float fsx = s.stage[t], fsy = s.stage[32 + t], fsz = s.stage[64 + t];
-                        const unsigned fh = screen_slots<K, PZ>(sc, fsx, fsy, fsz, q) & okmask;
-                        if (!__any_sync(FULL, fh != 0)) {
+                    const bool spec = !(((near0 | dirty) >> t) & 1u);       // lane t's speculation stands
+                    const int nbm = s.nb[n];
+                    unsigned hits_new = 0;
+                    float qsx = 0.f, qsy = 0.f, qsz = 0.f;
+                    if (spec) {
+                        // ---- one screen of the lane's K slots against the staged proposal
+                        qsx = s.stage[t]; qsy = s.stage[32 + t]; qsz = s.stage[64 + t];
+                        hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
+                        if (!__any_sync(FULL, hits_new != 0)) {
                             const bool facc = (acc0 >> t) & 1u;
+                            if (lane == 0) cnt += nbm;   // in-cutoff pairs of the old position (the reference evaluates them)
                             if (facc) {
+                                if (nbm) {               // medium path: the old partners forget this particle
+                                    __syncwarp();
+                                    dirty |= __ballot_sync(FULL, drop_old_partners(n, okmask));
+                                    __syncwarp();
+                                }
                                 if (lane == t) {         // the owner: its registers hold the proposal and its energy/force
                                     s.x[n] = p_qx; s.y[n] = p_qy; s.z[n] = p_qz;
-                                    s.ce[n] = p_Un; s.cfx[n] = 0.0; s.cfy[n] = 0.0; s.cfz[n] = p_fz;
-                                    q.set(0, fsx, fsy, fsz);
+                                    s.ce[n] = 4.0 * p_ew; s.cfx[n] = 0.0; s.cfy[n] = 0.0; s.cfz[n] = p_fz;
+                                    s.nb[n] = 0;
+                                    q.set(0, qsx, qsy, qsz);
                                     dE += p_dU;         // SMC.c:341, summed per lane, reduced at the end of the sweep
                                 }
                                 nacc++;
@@ -421,36 +451,30 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                             continue;
                         }
                     }
-                    // ---- general path: everything about this trial is (re)computed from the caches as they stand
+                    // ---- general path
                     __syncwarp();
-                    const int nbm = s.nb[n];
-                    double dX, dY, dZ, qx, qy, qz;
-                    {
-                        // proposal from the cached force of particle n (SMC.c:303-316)
-                        dX = fma(s.cfx[n], AoT, __shfl_sync(FULL, g0, t));
-                        dY = fma(s.cfy[n], AoT, __shfl_sync(FULL, g1, t));
-                        dZ = fma(s.cfz[n], AoT, __shfl_sync(FULL, g2, t));
+                    // proposal from the cached force of particle n (SMC.c:303-316)
+                    const double dX = fma(s.cfx[n], AoT, __shfl_sync(FULL, g0, t));
+                    const double dY = fma(s.cfy[n], AoT, __shfl_sync(FULL, g1, t));
+                    const double dZ = fma(s.cfz[n], AoT, __shfl_sync(FULL, g2, t));
+                    double qx, qy, qz, ew = 0.0, fzw = 0.0, dzw = 0.0;
+                    bool near = false;
+                    if (spec) {                          // as lane t speculated them: same values, no recomputation
+                        qx = __shfl_sync(FULL, p_qx, t); qy = __shfl_sync(FULL, p_qy, t); qz = __shfl_sync(FULL, p_qz, t);
+                        ew = __shfl_sync(FULL, p_ew, t); fzw = __shfl_sync(FULL, p_fz, t);
+                    } else {
                         qx = min_image<false>(s.x[n] + dX, b.L, b.invL);
                         qy = min_image<false>(s.y[n] + dY, b.L, b.invL);
                         qz = s.z[n] + dZ;
                         if (PZ) qz = min_image<false>(qz, b.Lz, b.invLz);
+                        qsx = (float)(qx * b.invL); qsy = (float)(qy * b.invL); qsz = (float)(qz * b.invL);
+                        if (b.wall) {                    // flat wall at the proposal: uniform, no cutoff
+                            dzw = wall_dz<false>(b, qz);
+                            near = dzw * dzw < b.rc2;
+                            add_zwall(b, dzw, ew, fzw);
+                        }
+                        hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
                     }
-                    const float qsx = (float)(qx * b.invL), qsy = (float)(qy * b.invL), qsz = (float)(qz * b.invL);
-
-                    // flat wall at the proposal: uniform, no cutoff; started early, off the pair loop's path
-                    double ew = 0.0, fzw = 0.0, dzw = 0.0;
-                    bool near = false;
-                    if (b.wall) {
-                        dzw = wall_dz<false>(b, qz);
-                        near = dzw * dzw < b.rc2;
-                        add_zwall(b, dzw, ew, fzw);
-                    }
-
-                    // one pass: the proposed position (always) and the old one (only if it has partners)
-                    unsigned hits_new, hits_old = 0;
-                    if (nbm)
-                        hits_old = screen_slots<K, PZ>(sc, (float)(s.x[n] * b.invL), (float)(s.y[n] * b.invL), (float)(s.z[n] * b.invL), q) & okmask;
-                    hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
 
                     // gas-phase fast path: nobody in range of the proposal -> all pair and site sums are exactly 0
                     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
@@ -483,20 +507,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                     if (acc) {
                         // partners lose the old pair terms and gain the new ones (force on j from n = -g d)
                         bool touched = false;           // physical slot 0 = the slot being visited: its speculation is void
-                        if (nbm) {
-                            const double px = s.x[n], py = s.y[n], pz = s.z[n];
-                            while (hits_old) {
-                                const int k = __ffs(hits_old) - 1;
-                                hits_old &= hits_old - 1;
-                                const int j = particle_of(k);
-                                double et, hx, hy, hz;
-                                if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
-                                    s.ce[j] -= 4.0 * et; s.cfx[j] += hx; s.cfy[j] += hy; s.cfz[j] += hz;
-                                    s.nb[j] -= 1;
-                                    touched |= (k == 0);
-                                }
-                            }
-                        }
+                        if (nbm) touched = drop_old_partners(n, okmask);
                         int nbn = 0;
                         if (work) {
                             unsigned hn = in_new;
