@@ -1,4 +1,1 @@
-python -m pytest tests/test_gpu_sweep.py tests/test_gpu_golden.py tests/test_gpu_observables.py tests/test_gpu_dropin.py -m gpu -q -x 2>&1 | tail -4
-python bench.py --steps 5 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('batched', d['value'], d['kernel_ms_per_step'], d['gather_ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['thermalised'])"
+python -m pytest tests/test_gpu_equilibrium.py -m gpu -q -x -s > gpurun_out/eq.log 2>&1; grep -n "<E>" gpurun_out/eq.log | head
