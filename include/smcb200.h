@@ -184,6 +184,16 @@ int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void 
 int smcb_get_rbin(smcb_engine *e, int32_t *rbin);
 int smcb_set_rbin(smcb_engine *e, const int32_t *rbin);
 
+/* ---- checkpoint / resume --------------------------------------------------
+ * The reference restarts from last_state_*.csv: positions only, %0.12f text (main.c:98-109,163-170;
+ * the drop-in keeps that format).  The batched engine adds a binary checkpoint of EVERYTHING a
+ * bit-identical continuation needs: exact positions, running energies, accept/trial counters, the
+ * Philox stream identity (seed, chain0, next step), Rbin and the observable block.  A run that is
+ * saved, destroyed, re-created with the same (nchains, nparticles, nsites_side), given the same
+ * smcb_set_params and loaded continues exactly as the uninterrupted run would. */
+int smcb_checkpoint_save(smcb_engine *e, const char *path);
+int smcb_checkpoint_load(smcb_engine *e, const char *path);
+
 /* ---- measurement -------------------------------------------------------- */
 /* device time (ms, CUDA events on the engine's stream) of the kernels launched
  * by the last smcb_sweep* / smcb_step_allparticle* / smcb_evaluate call, and

@@ -107,6 +107,35 @@ static int need_ready(smcb_engine *e)
     return SMCB_OK;
 }
 
+namespace {
+struct CkptHeader {
+    char magic[8];                 // "SMCB200\0"
+    uint32_t version, C, N, M, ngroups, nebins;
+    uint32_t chain0, pad_;
+    uint64_t seed, step;
+    double step_scale, e_lo, e_hi;
+    uint64_t n_counters, n_moments;
+};
+
+template <typename T>
+int put(FILE *f, const T *dev, size_t n, cudaStream_t st, std::vector<unsigned char> &buf)
+{
+    buf.resize(n * sizeof(T));
+    if (cudaMemcpyAsync(buf.data(), dev, buf.size(), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    return fwrite(buf.data(), 1, buf.size(), f) == buf.size() ? 0 : -2;
+}
+
+template <typename T>
+int get(FILE *f, T *dev, size_t n, cudaStream_t st, std::vector<unsigned char> &buf)
+{
+    buf.resize(n * sizeof(T));
+    if (fread(buf.data(), 1, buf.size(), f) != buf.size()) return -2;
+    if (cudaMemcpyAsync(dev, buf.data(), buf.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
+}
+}  // namespace
+
 extern "C" {
 
 const char *smcb_last_error(void) { return g_err.c_str(); }
@@ -653,6 +682,75 @@ int smcb_set_rbin(smcb_engine *e, const int32_t *rbin)
     if (!rbin) return fail(SMCB_ERR_ARG, "rbin is null");
     CK(cudaMemcpyAsync(e->rbin.p, rbin, (size_t)e->C * e->N * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+// --------------------------------------------------------- checkpoint / resume
+
+int smcb_checkpoint_save(smcb_engine *e, const char *path)
+{
+    int rc = need_ready(e);
+    if (rc) return rc;
+    if (!path) return fail(SMCB_ERR_ARG, "path is null");
+    if (!e->energy_valid && (rc = refresh_energy(e, SMCB_FAST))) return rc;
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(SMCB_ERR_ARG, "cannot open %s for writing", path);
+    CkptHeader h{};
+    memcpy(h.magic, "SMCB200", 8);
+    h.version = 1; h.C = e->C; h.N = e->N; h.M = e->M; h.ngroups = e->ngroups; h.nebins = e->nebins;
+    h.chain0 = e->chain0; h.seed = e->seed; h.step = e->step; h.step_scale = e->step_scale;
+    h.e_lo = e->e_lo; h.e_hi = e->e_hi;
+    h.n_counters = e->u64_per_group() * e->ngroups; h.n_moments = e->f64_per_group() * e->ngroups;
+    std::vector<unsigned char> buf;
+    int w = fwrite(&h, sizeof h, 1, f) == 1 ? 0 : -2;
+    if (!w) w = put(f, e->pos.p, (size_t)e->C * 3 * e->Npad, e->stream, buf);
+    if (!w) w = put(f, e->E.p, (size_t)e->C, e->stream, buf);
+    if (!w) w = put(f, e->nacc.p, (size_t)e->C, e->stream, buf);
+    if (!w) w = put(f, e->ntri.p, (size_t)e->C, e->stream, buf);
+    if (!w) w = put(f, e->rbin.p, (size_t)e->C * e->N, e->stream, buf);
+    if (!w) w = put(f, e->counters.p, (size_t)h.n_counters, e->stream, buf);
+    if (!w) w = put(f, e->moments.p, (size_t)h.n_moments, e->stream, buf);
+    if (fclose(f) != 0 && !w) w = -2;
+    if (w == -1) return fail(SMCB_ERR_CUDA, "checkpoint_save: device copy failed");
+    if (w) return fail(SMCB_ERR_ARG, "checkpoint_save: short write to %s", path);
+    return SMCB_OK;
+}
+
+int smcb_checkpoint_load(smcb_engine *e, const char *path)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->have_params) return fail(SMCB_ERR_STATE, "smcb_set_params must be called before smcb_checkpoint_load");
+    if (!path) return fail(SMCB_ERR_ARG, "path is null");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(SMCB_ERR_ARG, "cannot open %s", path);
+    CkptHeader h{};
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SMCB200", 8) != 0 || h.version != 1) {
+        fclose(f);
+        return fail(SMCB_ERR_ARG, "%s is not a smcb200 checkpoint (version 1)", path);
+    }
+    if ((int)h.C != e->C || (int)h.N != e->N || (int)h.M != e->M || (int)h.ngroups != e->ngroups) {
+        fclose(f);
+        return fail(SMCB_ERR_ARG, "checkpoint is for %u chains x N=%u, M=%u, %u groups; engine has %d x N=%d, M=%d, %d groups",
+                    h.C, h.N, h.M, h.ngroups, e->C, e->N, e->M, e->ngroups);
+    }
+    if ((int)h.nebins != e->nebins || h.e_lo != e->e_lo || h.e_hi != e->e_hi) {
+        e->nebins = (int)h.nebins; e->e_lo = h.e_lo; e->e_hi = h.e_hi;
+        if ((rc = obs_alloc(e))) { fclose(f); return rc; }
+    }
+    std::vector<unsigned char> buf;
+    int w = get(f, e->pos.p, (size_t)e->C * 3 * e->Npad, e->stream, buf);
+    if (!w) w = get(f, e->E.p, (size_t)e->C, e->stream, buf);
+    if (!w) w = get(f, e->nacc.p, (size_t)e->C, e->stream, buf);
+    if (!w) w = get(f, e->ntri.p, (size_t)e->C, e->stream, buf);
+    if (!w) w = get(f, e->rbin.p, (size_t)e->C * e->N, e->stream, buf);
+    if (!w) w = get(f, e->counters.p, (size_t)h.n_counters, e->stream, buf);
+    if (!w) w = get(f, e->moments.p, (size_t)h.n_moments, e->stream, buf);
+    fclose(f);
+    if (w == -1) return fail(SMCB_ERR_CUDA, "checkpoint_load: device copy failed");
+    if (w) return fail(SMCB_ERR_ARG, "checkpoint_load: %s is truncated", path);
+    e->seed = h.seed; e->chain0 = h.chain0; e->step = h.step; e->step_scale = h.step_scale;
+    e->have_pos = true; e->energy_valid = true; e->forces_valid = false;
     return SMCB_OK;
 }
 

@@ -92,6 +92,8 @@ def load_library():
         "smcb_obs_export_device": [P, P, P],
         "smcb_obs_import_device": [P, P, P],
         "smcb_get_rbin": [P, P],
+        "smcb_checkpoint_save": [P, C.c_char_p],
+        "smcb_checkpoint_load": [P, C.c_char_p],
         "smcb_last_kernel_ms": [P, C.POINTER(C.c_float), C.POINTER(C.c_int)],
         "smcb_last_pair_counts": [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
         "smcb_measure_fp64_peak": [P, dp, C.POINTER(C.c_float)],
@@ -321,6 +323,13 @@ class Engine:
     def set_rbin(self, rb):
         rb = np.ascontiguousarray(rb, dtype=np.int32)
         self._ck(self.lib.smcb_set_rbin(self._h, _ptr(rb)))
+
+    # -- checkpoint / resume ------------------------------------------------------------
+    def checkpoint_save(self, path):
+        self._ck(self.lib.smcb_checkpoint_save(self._h, os.fsencode(path)))
+
+    def checkpoint_load(self, path):
+        self._ck(self.lib.smcb_checkpoint_load(self._h, os.fsencode(path)))
 
     # -- measurement -----------------------------------------------------------------
     def last_kernel_ms(self):

@@ -102,3 +102,47 @@ def test_same_stream_same_chain_and_sharding():
             res[name] = eng.get_positions()
     np.testing.assert_array_equal(res["full"][:4], res["lo"])
     np.testing.assert_array_equal(res["full"][4:], res["hi"])
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """binary checkpoint (positions, energies, counters, Philox stream position, Rbin, observable block):
+    save -> destroy -> create -> load continues exactly like the uninterrupted run (the
+    reference restores positions only, main.c:98-109)"""
+    N, M = 108, 3
+    L, Lz = geom(N)
+    orc = Oracle()
+    R0, _ = orc.initialize_box(L, Lz, N)
+    par = smcb.default_params(L=L, Lz=Lz, T=1.1, A=1.1)
+
+    def fresh():
+        eng = smcb.Engine(6, N, M)
+        eng.set_params(par, GOLDEN_W_M3)
+        return eng
+
+    with fresh() as eng:
+        eng.broadcast_positions(R0)
+        eng.set_rng(4242, 10, 0)
+        eng.sweep(7, smcb.FAST); eng.gather()
+        eng.sweep(5, smcb.FAST); eng.gather()
+        ref_R, ref_state, ref_obs, ref_rbin = eng.get_positions(), eng.chain_state(), eng.obs_get()[0], eng.rbin()
+    ck = tmp_path / "chains.smcb"
+    with fresh() as eng:
+        eng.broadcast_positions(R0)
+        eng.set_rng(4242, 10, 0)
+        eng.sweep(7, smcb.FAST); eng.gather()
+        eng.checkpoint_save(ck)
+    with fresh() as eng:
+        eng.checkpoint_load(ck)
+        eng.sweep(5, smcb.FAST); eng.gather()
+        np.testing.assert_array_equal(eng.get_positions(), ref_R)
+        for a, b in zip(eng.chain_state(), ref_state):
+            np.testing.assert_array_equal(a, b)
+        o = eng.obs_get()[0]
+        for k in ("D", "Mu", "zprof", "ehist"):
+            np.testing.assert_array_equal(o[k], ref_obs[k])
+        assert o["nsamples"] == ref_obs["nsamples"] and o["sumE"] == ref_obs["sumE"]
+        np.testing.assert_array_equal(eng.rbin(), ref_rbin)
+    with smcb.Engine(5, N, M) as eng:                       # wrong shape: refused, not silently reshaped
+        eng.set_params(par, GOLDEN_W_M3)
+        with pytest.raises(smcb.SmcbError):
+            eng.checkpoint_load(ck)
