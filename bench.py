@@ -53,9 +53,11 @@ def parse():
     ap.add_argument("--sweeps-per-step", type=int, default=40)
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--kernel", default="sweep", choices=["sweep", "allparticle"])
-    ap.add_argument("--workload", default="batched", choices=["batched", "largeN"],
-                    help="batched: 8192 chains x N=256 per GPU (configs[2], the headline); largeN: 256 chains x N=4096 in "
-                         "total, sharded over the GPUs (configs[4], all-particle kernel with thread-block clusters)")
+    ap.add_argument("--workload", default="batched", choices=["batched", "grid", "largeN"],
+                    help="batched: 8192 chains x N=256 per GPU (configs[2], the headline); grid: 65536 chains in total on a "
+                         "16 T x 4 Lz x 4 wall-strength grid x 256 replicas, sharded over the GPUs, one observable group per "
+                         "grid point (configs[3]); largeN: 256 chains x N=4096 in total, sharded over the GPUs (configs[4], "
+                         "all-particle kernel with thread-block clusters)")
     ap.add_argument("--thermalise", type=int, default=2000,
                     help="sweeps with 2A (sMC's thermalisation, SMC.c:110-125) before the extra 'thermalised' timing leg; 0 = skip")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
@@ -236,6 +238,15 @@ def main():
         N, args.kernel = 4096, "allparticle"
         Cn = args.chains or smcb.shard_chains(256, world, rank).nchains      # --chains 32 emulates one rank of 8
         total_largeN = float(world) * Cn if args.chains else 256.0
+    grid = None
+    if args.workload == "grid":                     # configs[3]: the T / density / wall grid the MPI ranks used to split
+        total_grid = (args.chains * world) if args.chains else 65536
+        shard = smcb.shard_chains(total_grid, world, rank)
+        Cn = shard.nchains
+        temps = [0.7 + 0.05 * i for i in range(16)]
+        lzs = [120.0, 160.0, 200.0, 240.0]
+        walls = [0, 1, 2, 3]                         # wall tables: ymin = 2.0, 2.67, 3.33, 4.0 (main.c:76 uses 3.0 +- 0.5)
+        grid = (shard, temps, lzs, walls, total_grid)
     mode = smcb.STRICT if args.mode == "strict" else smcb.FAST
     A = TEMP if args.kernel == "sweep" else (2e-4 if N <= 256 else 2e-6)
 
@@ -252,10 +263,18 @@ def main():
     R0 = X.reshape(-1)
 
     eng = smcb.Engine(Cn, N, M_SITES, device=local)
-    eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=A), GOLDEN_W_M3, ngroups=1)
+    if grid:
+        shard, temps, lzs, walls, total_grid = grid
+        params, ngroups = smcb.grid_chain_params(shard, temps, lzs, walls, L=L_BOX)
+        Wt = np.concatenate([GOLDEN_W_M3 * (ym / 3.0) for ym in (2.0, 8.0 / 3.0, 10.0 / 3.0, 4.0)])
+        eng.set_params(params, Wt, ngroups=ngroups)
+        chain0 = shard.chain0
+    else:
+        eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=A), GOLDEN_W_M3, ngroups=1)
+        chain0 = rank * Cn
     eng.obs_configure(nebins=64, e_lo=-8.0, e_hi=2.0)
     eng.broadcast_positions(R0)
-    eng.set_rng(12345, rank * Cn, 0)
+    eng.set_rng(12345, chain0, 0)
     info = eng.device_info()
     lay = eng.obs_layout()
 
@@ -323,7 +342,7 @@ def main():
         dev_ms = smcb.max_over_ranks(k_tot + g_tot + c_tot, device="cuda")
         k_max = smcb.max_over_ranks(k_tot, device="cuda")
         unit_pairs = pairs_per_sweep(N) if kernel == "sweep" else float(N) * (N - 1)
-        total_chains = float(world) * Cn if args.workload == "batched" else total_largeN
+        total_chains = float(world) * Cn if args.workload == "batched" else (float(grid[4]) if grid else total_largeN)
         chain_steps = total_chains * S * nsteps
         flops = FLOPS_PAIR * pairs_tot + FLOPS_INCUT * pairs_cut
         return {"value": chain_steps * unit_pairs / (dev_ms * 1e-3), "chain_steps_per_s": chain_steps / (dev_ms * 1e-3),
@@ -358,7 +377,7 @@ def main():
             e2e_step()
         barrier()
         te = smcb.max_over_ranks(time.perf_counter() - t0, device="cuda")
-        total_chains = float(world) * Cn if args.workload == "batched" else total_largeN
+        total_chains = float(world) * Cn if args.workload == "batched" else (float(grid[4]) if grid else total_largeN)
         e2e = {"value": total_chains * S * nsteps_e2e * main["unit_pairs"] / te, "unit": "pair-interactions/s",
                "chain_steps_per_s": total_chains * S * nsteps_e2e / te, "steps": nsteps_e2e,
                "h2d_bytes_per_step": int(Cn * 3 * N * 8), "d2h_bytes_per_step": int(Cn * 3 * N * 8 + Cn * 24),
@@ -399,10 +418,12 @@ def main():
             "chain_steps_per_s": main["chain_steps_per_s"],
             "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": main["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak" if args.workload == "batched" else "strong", "vs_baseline": None,
+            "scaling": "weak" if args.workload == "batched" or (grid and args.chains) else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": (f"{Cn} chains/GPU x N={N} with wall (BASELINE configs[2])" if args.workload == "batched"
-                                    else f"{int(total_largeN)} chains x N={N} with wall in total (BASELINE configs[4]), {Cn} on this rank")
+                                    else f"{grid[4]} chains x N={N} on a 16 T x 4 Lz x 4 wall grid x replicas (BASELINE configs[3]), "
+                                         f"{Cn} on this rank, {len(grid[1]) * len(grid[2]) * len(grid[3])} observable groups all-reduced"
+                                    if grid else f"{int(total_largeN)} chains x N={N} with wall in total (BASELINE configs[4]), {Cn} on this rank")
                                    + f", {args.kernel} kernel, {args.mode}",
                        "chains_per_gpu": Cn, "N": N, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": A,
                        "sweeps_per_step": S, "start": "initializeBox fcc lattice + warm-up steps",

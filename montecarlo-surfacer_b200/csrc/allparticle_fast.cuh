@@ -278,6 +278,30 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
     }
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP): one contiguous tile global -> shared, completion on an mbarrier.
+// A chain's positions are one contiguous [3][Npad] block in HBM (SoA, Npad a multiple of 32: 16-byte aligned and
+// sized), exactly the layout of StepSmem::x/y/z, so the whole j-side tile arrives with ONE asynchronous copy issued
+// by one thread while the others fill the pad slots; nobody spends LSU instructions or registers on it.
+__device__ __forceinline__ void tile_load_begin(double *smem_dst, const double *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar), dst_a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_a), "l"(gsrc), "r"(bytes), "r"(bar_a) : "memory");
+}
+
+__device__ __forceinline__ void tile_load_wait(uint64_t *bar)
+{
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar_a) : "memory");
+    }
+}
+
 // ---- FAST static evaluation (rows a2-a10 of the survey) with the same screened pair loop ----------------
 // `parts` blocks per chain (plain grid, no cluster): block `part` owns molecules part, part+parts, ...; every
 // block stages the whole chain.  Chain totals: each block leaves its partial sums in `partials`, and the LAST
@@ -302,11 +326,14 @@ __device__ __forceinline__ void evaluate_fast_body(const DevChains &d, const Eva
     const ScreenConsts sc = make_screen(b);
     const double *W = d.W + (size_t)cp.wall * 2 * d.M * d.M;
     const double *P = d.pos + (size_t)chain * 3 * Npad;
-    for (int j = tid; j < Npad; j += T_) {
-        const bool in = j < N;
-        const double X = in ? P[j] : 0.0, Y = in ? P[Npad + j] : 0.0, Z = in ? P[2 * Npad + j] : 0.0;
-        s.x[j] = X; s.y[j] = Y; s.z[j] = Z;
-        s.fx[j] = (float)(X * b.invL); s.fy[j] = (float)(Y * b.invL); s.fz[j] = in ? (float)(Z * b.invL) : 3.0e18f;
+    // the chain's [3][Npad] position block -> s.x/s.y/s.z in one bulk-async copy (pad slots hold 0 in HBM)
+    __shared__ uint64_t s_bar;
+    if (tid == 0) tile_load_begin(s.x, P, (uint32_t)(3 * Npad * sizeof(double)), &s_bar);
+    __syncthreads();                                      // the barrier is initialised before anyone polls it
+    tile_load_wait(&s_bar);
+    for (int j = tid; j < Npad; j += T_) {                // screen-precision copy in box units; pad slots far away
+        s.fx[j] = (float)(s.x[j] * b.invL); s.fy[j] = (float)(s.y[j] * b.invL);
+        s.fz[j] = j < N ? (float)(s.z[j] * b.invL) : 3.0e18f;
     }
     __syncthreads();
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
