@@ -159,7 +159,10 @@ int smcb_reset_counters(smcb_engine *e);
  *   n, sum E, sum E^2, sum P, sum P^2 (P = pressure + wallsPressure as the
  *   reference writes them, SMC.c:140).
  * The block is one contiguous array of uint64 counters followed by doubles per
- * group (layout from smcb_obs_layout); it is the ONLY thing ranks all-reduce. */
+ * group (layout from smcb_obs_layout); it is the ONLY thing ranks all-reduce.
+ * Counters are exact (integer atomics).  The moments are accumulated over chains with
+ * double-precision atomics, so their last bits depend on the order chains retire; chain
+ * state (positions, energies, accept counts) is always bit-reproducible. */
 typedef struct smcb_obs_layout {
     int ngroups;
     int nvox;            /* 33*33*33                                   */

@@ -46,7 +46,10 @@ __device__ __forceinline__ double min_image(double d, double P, double invP)
         // k is a small integer, so P*k is exact and the FMA rounds once, like the
         // reference; d*invP can differ from d/P only within an ulp of a half-integer,
         // where |d - P*k| ~ P/2 is outside the cutoff either way.
-        double k = rint(d * invP);
+        // rint by the 1.5*2^52 trick: two DADDs on the FP64 pipe (16 cycles) instead of FRND.F64 on the XU
+        // pipe (37 cycles latency, 9 cycles per warp instruction; profiles/r01/microbench_fp64_lat.txt).
+        // Exact round-to-nearest-even for |d/P| < 2^51, i.e. the same k as rint().
+        const double k = __dsub_rn(__dadd_rn(d * invP, 6755399441055744.0), 6755399441055744.0);
         return fma(-P, k, d);
     }
 }

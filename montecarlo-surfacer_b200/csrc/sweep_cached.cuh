@@ -492,7 +492,22 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                             }
                         }
                         if (near) add_sites(b, s, lane, MMpad, qx, qy, dzw, e, fx, fy, fz);
-                        warp_sum4(lane, e, fx, fy, fz);
+                        // Sum over the warp.  Usually one or two lanes hold a partner: their four partial sums are
+                        // fetched with independent shuffles (one shuffle latency) instead of the five dependent
+                        // levels of the butterfly; lane order is fixed, so the result is deterministic either way.
+                        unsigned holders = __ballot_sync(FULL, in_new != 0 || (near && lane < MM));
+                        if (__popc(holders) <= 2) {
+                            double te = 0.0, tx = 0.0, ty = 0.0, tz = 0.0;
+                            while (holders) {
+                                const int src = __ffs(holders) - 1;
+                                holders &= holders - 1;
+                                te += __shfl_sync(FULL, e, src); tx += __shfl_sync(FULL, fx, src);
+                                ty += __shfl_sync(FULL, fy, src); tz += __shfl_sync(FULL, fz, src);
+                            }
+                            e = te; fx = tx; fy = ty; fz = tz;
+                        } else {
+                            warp_sum4(lane, e, fx, fy, fz);
+                        }
                     }
                     const double Un = 4.0 * (e + ew), Fnx = fx, Fny = fy, Fnz = fz + fzw;                 // SMC.c:319-321
 
