@@ -33,16 +33,34 @@ struct StepSmem {
     float *fx, *fy, *fz;      // the same in box units, screen precision      [3][Npad]
     double *scratch;          // block_sum scratch                            [8*32]
     double *part;             // this block's partial MH sums (read by the cluster peers) [4]
-    __device__ __forceinline__ void carve(double *base, int Npad)
+    // half-shell extras (HALF kernels only): the screen-precision coordinates once more as CIRCULAR arrays
+    // (index m holds particle m mod N) in two copies, B shifted by one (B[m] = A[m+1]), so that the pair of
+    // partners (i+1+2k, i+2+2k) of any i is one aligned float2; and the hit words of phase 1
+    float *cbase;                   // [3 components][2 copies][NE]
+    unsigned *fw, *bw;              // forward / backward hit words [N][NW]
+    int NW, NE;
+    __device__ __forceinline__ float *circ(int comp, int copy) const { return cbase + (2 * comp + copy) * NE; }
+    static __host__ __device__ int half_words(int N) { return (N / 2 + 31) / 32; }
+    static __host__ __device__ int half_ext(int N) { return (N + 32 * half_words(N) + 3) & ~1; }
+    __device__ __forceinline__ void carve(double *base, int Npad, int N = 0, bool half = false)
     {
         x = base; y = x + Npad; z = y + Npad;
         scratch = z + Npad;
         part = scratch + 8 * 32;
         fx = reinterpret_cast<float *>(part + 4); fy = fx + Npad; fz = fy + Npad;
+        NW = NE = 0;
+        if (half) {
+            NW = half_words(N); NE = half_ext(N);
+            cbase = fz + Npad;
+            fw = reinterpret_cast<unsigned *>(cbase + 6 * NE);
+            bw = fw + (size_t)N * NW;
+        }
     }
-    static __host__ __device__ size_t bytes(int Npad)
+    static __host__ __device__ size_t bytes(int Npad, int N = 0, bool half = false)
     {
-        return (size_t)(3 * Npad + 8 * 32 + 4) * sizeof(double) + (size_t)3 * Npad * sizeof(float);
+        size_t b = (size_t)(3 * Npad + 8 * 32 + 4) * sizeof(double) + (size_t)3 * Npad * sizeof(float);
+        if (half) b += (size_t)6 * half_ext(N) * sizeof(float) + (size_t)2 * N * half_words(N) * sizeof(unsigned);
+        return b;
     }
 };
 
@@ -130,15 +148,91 @@ __device__ __forceinline__ double wall_point_fast(const Box &b, const double *__
     return e;
 }
 
-// FED: host-fed noise (parity); PZ: bulk mode (z periodic); CL: blocks per chain (cluster size)
-template <bool FED, bool PZ, int CL>
+// ---- half-shell screen (Newton's third law for the screen) -------------------------------------------------
+// Every unordered pair is screened ONCE: molecule i looks at the partners i+1 .. i+H (indices mod N, H = N/2;
+// for even N the offset N/2 only from the lower half), which halves the O(N^2) part of a step.  A hit at offset
+// d is recorded for both members: bit d-1 of fw[i] and, with a shared-memory atomicOr (order-independent), bit
+// d-1 of bw[i+d].  Phase 2 then lets every molecule evaluate ALL its partners itself, forward offsets ascending,
+// then backward offsets ascending - a fixed order, no floating-point atomics, and the pair terms seen from both
+// members are exact negatives of each other.
+template <bool PZ>
+__device__ __forceinline__ void half_shell_screen(const ScreenConsts &sc, const StepSmem &s, int N, int i, float qx, float qy, float qz)
+{
+    const int H = N / 2, start = i + 1, odd = start & 1;
+    const int Hi = (!(N & 1) && i >= H) ? H - 1 : H;          // valid offsets of this molecule
+    const float2 *X2 = reinterpret_cast<const float2 *>(s.circ(0, odd)) + (start >> 1);
+    const float2 *Y2 = reinterpret_cast<const float2 *>(s.circ(1, odd)) + (start >> 1);
+    const float2 *Z2 = reinterpret_cast<const float2 *>(s.circ(2, odd)) + (start >> 1);
+    const float2 ax = make_float2(qx, qx), ay = make_float2(qy, qy), az = make_float2(qz, qz);
+    const float2 MG = make_float2(12582912.f, 12582912.f);
+    for (int c = 0; c < s.NW; c++) {
+        unsigned hits = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int j2 = c * 16 + k;
+            float2 sx = sub2(ax, X2[j2]);
+            sx = sub2(sx, sub2(add2(sx, MG), MG));
+            float2 sy = sub2(ay, Y2[j2]);
+            sy = sub2(sy, sub2(add2(sy, MG), MG));
+            float2 sz = sub2(az, Z2[j2]);
+            if (PZ) {
+                const float2 t = mul2(sz, make_float2(sc.inv_zper, sc.inv_zper));
+                sz = fma2(sub2(add2(t, MG), MG), make_float2(-sc.zper, -sc.zper), sz);
+            }
+            const float2 r2 = fma2(sz, sz, fma2(sy, sy, mul2(sx, sx)));
+            if (r2.x < sc.rc2s) hits |= 1u << (2 * k);
+            if (r2.y < sc.rc2s) hits |= 2u << (2 * k);
+        }
+        const int rem = Hi - 32 * c;                          // offsets 32c+1 .. 32c+32 that exist
+        if (rem < 32) hits &= rem <= 0 ? 0u : ((1u << rem) - 1u);
+        s.fw[i * s.NW + c] = hits;
+        while (hits) {
+            const int bit = __ffs(hits) - 1;
+            hits &= hits - 1;
+            int j = i + 32 * c + bit + 1;
+            if (j >= N) j -= N;
+            atomicOr(s.bw + j * s.NW + c, 1u << bit);
+        }
+    }
+}
+
+__device__ __forceinline__ void half_shell_exact(const Box &b, const StepSmem &s, int N, int i, double px, double py, double pz,
+                                                 double &e_lj, double &fx, double &fy, double &fz, unsigned &cnt)
+{
+    double e = 0.0;
+    fx = fy = fz = 0.0;
+    for (int dir = 0; dir < 2; dir++) {
+        const unsigned *words = (dir == 0 ? s.fw : s.bw) + i * s.NW;
+        for (int c = 0; c < s.NW; c++) {
+            unsigned w = words[c];
+            while (w) {
+                const int d = 32 * c + __ffs(w);
+                w &= w - 1;
+                int j = dir == 0 ? i + d : i - d;
+                if (j >= N) j -= N;
+                if (j < 0) j += N;
+                double et, gx, gy, gz;
+                if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
+                    e += et; fx += gx; fy += gy; fz += gz;
+                    cnt++;
+                }
+            }
+        }
+    }
+    e_lj = 4.0 * e;
+}
+
+// FED: host-fed noise (parity); PZ: bulk mode (z periodic); CL: blocks per chain (cluster size);
+// HALF: half-shell screen (one block per chain, N <= 512)
+template <bool FED, bool PZ, int CL, bool HALF>
 __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const StepArgs &a)
 {
+    static_assert(!HALF || CL == 1, "the half-shell screen keeps a chain in one block");
     const int chain = blockIdx.x / CL, part = blockIdx.x % CL;
     const int N = d.N, Npad = d.Npad, tid = threadIdx.x, T_ = blockDim.x;
     extern __shared__ double sm[];
     StepSmem s;
-    s.carve(sm, Npad);
+    s.carve(sm, Npad, N, HALF);
     __shared__ int s_accept;
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, d.step_scale);
@@ -171,10 +265,24 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
     // forces / energies of this block's molecules at the staged configuration; returns the MH partial sums
     auto evaluate_owned = [&](double *Fout, const double *Fold, bool with_mh, double (&t)[3]) {
         t[0] = t[1] = t[2] = 0.0;
+        if (HALF) {
+            // circular screen-precision copies (two alignments) and cleared backward words, then phase 1
+            for (int m = tid; m < s.NE; m += T_) {
+                int j0 = m; while (j0 >= N) j0 -= N;
+                int j1 = m + 1; while (j1 >= N) j1 -= N;
+                s.circ(0, 0)[m] = s.fx[j0]; s.circ(1, 0)[m] = s.fy[j0]; s.circ(2, 0)[m] = s.fz[j0];
+                s.circ(0, 1)[m] = s.fx[j1]; s.circ(1, 1)[m] = s.fy[j1]; s.circ(2, 1)[m] = s.fz[j1];
+            }
+            for (int m = tid; m < N * s.NW; m += T_) s.bw[m] = 0u;
+            __syncthreads();
+            for (int i = tid; i < N; i += T_) half_shell_screen<PZ>(sc, s, N, i, s.fx[i], s.fy[i], s.fz[i]);
+            __syncthreads();
+        }
         for (int i = part + CL * tid; i < N; i += CL * T_) {
             const double px = s.x[i], py = s.y[i], pz = s.z[i];
             double e_lj, fx, fy, fz;
-            particle_vs_staged<PZ>(b, sc, s, N, Npad, i, px, py, pz, e_lj, fx, fy, fz, cnt);
+            if (HALF) half_shell_exact(b, s, N, i, px, py, pz, e_lj, fx, fy, fz, cnt);
+            else particle_vs_staged<PZ>(b, sc, s, N, Npad, i, px, py, pz, e_lj, fx, fy, fz, cnt);
             double e_wall = 0.0;
             if (b.wall) {
                 double wx = 0.0, wy = 0.0, wz = 0.0;
@@ -385,11 +493,11 @@ __global__ void __launch_bounds__(512) k_evaluate_fast(DevChains d, EvalOut o, E
 }
 #endif
 
-template <bool FED, int CL>
+template <bool FED, int CL, bool HALF>
 __global__ void __launch_bounds__(512) k_allparticle_fast(DevChains d, StepArgs a)
 {
-    if (chain_params(d, blockIdx.x / CL).flags & SMCB_PERIODIC_Z) allparticle_fast_body<FED, true, CL>(d, a);
-    else allparticle_fast_body<FED, false, CL>(d, a);
+    if (chain_params(d, blockIdx.x / CL).flags & SMCB_PERIODIC_Z) allparticle_fast_body<FED, true, CL, HALF>(d, a);
+    else allparticle_fast_body<FED, false, CL, HALF>(d, a);
 }
 
 }  // namespace smcb

@@ -100,11 +100,11 @@ static int allparticle_cluster(const DevChains &d)
     return cl;
 }
 
-template <bool FED, int CL>
+template <bool FED, int CL, bool HALF = false>
 static cudaError_t allparticle_fast_k(const DevChains &d, const StepArgs &a, cudaStream_t st)
 {
-    const size_t smem = StepSmem::bytes(d.Npad);
-    auto kern = k_allparticle_fast<FED, CL>;
+    const size_t smem = StepSmem::bytes(d.Npad, d.N, HALF);
+    auto kern = k_allparticle_fast<FED, CL, HALF>;
     cudaError_t err;
     if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
     int per = (d.N + CL - 1) / CL;
@@ -129,7 +129,11 @@ cudaError_t launch_allparticle_fast(bool fed, const DevChains &d, const StepArgs
     case 8: return fed ? allparticle_fast_k<true, 8>(d, a, st) : allparticle_fast_k<false, 8>(d, a, st);
     case 4: return fed ? allparticle_fast_k<true, 4>(d, a, st) : allparticle_fast_k<false, 4>(d, a, st);
     case 2: return fed ? allparticle_fast_k<true, 2>(d, a, st) : allparticle_fast_k<false, 2>(d, a, st);
-    default: return fed ? allparticle_fast_k<true, 1>(d, a, st) : allparticle_fast_k<false, 1>(d, a, st);
+    default:
+        // one block per chain: screen every unordered pair once (half shell) while the hit words fit comfortably
+        if (d.N <= 512 && !getenv("SMCB_FULL_SHELL"))
+            return fed ? allparticle_fast_k<true, 1, true>(d, a, st) : allparticle_fast_k<false, 1, true>(d, a, st);
+        return fed ? allparticle_fast_k<true, 1>(d, a, st) : allparticle_fast_k<false, 1>(d, a, st);
     }
 }
 #else
