@@ -88,7 +88,10 @@ int smcb_get_positions(smcb_engine *e, double *R);
 int smcb_broadcast_positions(smcb_engine *e, const double *R0);
 /* Philox4x32-10 stream identity: key = seed, counter carries (step, chain id,
  * particle).  chain0 is the global id of this engine's first chain so shards
- * of one job draw disjoint streams. */
+ * of one job draw disjoint streams.  SMCB_STRICT kernels turn the bits into
+ * Gaussians with a double-precision Box-Muller that the test oracle replays
+ * exactly; SMCB_FAST kernels use a single-precision Box-Muller on the same
+ * counter (csrc/philox.cuh) - a different, equally valid stream. */
 int smcb_set_rng(smcb_engine *e, uint64_t seed, uint32_t chain0, uint64_t step0);
 
 /* ---- static evaluation (rows a2-a10) ------------------------------------

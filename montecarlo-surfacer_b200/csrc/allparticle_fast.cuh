@@ -333,7 +333,7 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
                 const double *xi = a.xi + sci * 3 * N;
                 g0 = xi[3 * j]; g1 = xi[3 * j + 1]; g2 = xi[3 * j + 2];
             } else {
-                rng_particle_gauss(id, step, (uint32_t)j, g0, g1, g2);
+                rng_particle_gauss_f32(id, step, (uint32_t)j, g0, g1, g2);
                 g0 *= sigma; g1 *= sigma; g2 *= sigma;
             }
             const double dX = fma(Fc[j], AoT, g0), dY = fma(Fc[Npad + j], AoT, g1), dZ = fma(Fc[2 * Npad + j], AoT, g2);

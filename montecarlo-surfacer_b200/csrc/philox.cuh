@@ -7,7 +7,11 @@
 // orc_rng_step_scalars) replays the identical stream.
 //   key     = (seed_lo, seed_hi)
 //   counter = (step_lo, step_hi, chain, particle | tag << 28)
-//   tag 0,1 : the two blocks behind a particle's three N(0,1) numbers
+//   tag 0,1 : the two blocks behind a particle's three N(0,1) numbers (STRICT kernels: Box-Muller in double
+//             precision on 53-bit uniforms, replayed exactly by the oracle); the FAST kernels take all three
+//             from block 0 with a SINGLE-precision Box-Muller (32-bit uniforms, logf/sincospif, ~1e-7 relative;
+//             the tail reaches 6.6 sigma): the transform ran on the scarce FP64 pipe and cost as much as the
+//             half-shell pair screen of the all-particle step
 //   tag 2   : the particle's trial uniform (sweep kernel)
 //   tag 3   : per-step scalars (sweep offset, whole-chain uniform); particle = 0
 #pragma once
@@ -56,6 +60,23 @@ __device__ __forceinline__ void rng_particle_gauss(const RngId &id, unsigned lon
     g0 = r1 * c;
     g1 = r1 * s;
     g2 = r2 * cospi(2.0 * u4);
+}
+
+// FAST variant: three standard normals from ONE Philox block, single-precision transform, returned as doubles
+__device__ __forceinline__ void rng_particle_gauss_f32(const RngId &id, unsigned long long step, uint32_t particle,
+                                                       double &g0, double &g1, double &g2)
+{
+    uint32_t a[4];
+    philox4x32_10(static_cast<uint32_t>(step), static_cast<uint32_t>(step >> 32), id.chain, particle, id.k0, id.k1, a);
+    // (a + 1/2) / 2^32 in (0, 1]: one rounding in the fma, small values keep their full precision (the tail)
+    const float u1 = fmaf(static_cast<float>(a[0]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u3 = fmaf(static_cast<float>(a[2]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u3));
+    float sn, cs;
+    sincospif(static_cast<float>(a[1]) * 4.6566128730773926e-10f, &sn, &cs);      // angle 2 pi a1 / 2^32
+    g0 = static_cast<double>(r1 * cs);
+    g1 = static_cast<double>(r1 * sn);
+    g2 = static_cast<double>(r2 * cospif(static_cast<float>(a[3]) * 4.6566128730773926e-10f));
 }
 
 __device__ __forceinline__ double rng_particle_uniform(const RngId &id, unsigned long long step, uint32_t particle)

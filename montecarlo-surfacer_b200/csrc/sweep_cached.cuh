@@ -367,7 +367,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                         if (nn < 0) nn += N;
                         ul = a.u[sci * N + nn];
                     } else {
-                        rng_particle_gauss(id, step, (uint32_t)nl, g0, g1, g2);
+                        rng_particle_gauss_f32(id, step, (uint32_t)nl, g0, g1, g2);
                         g0 *= sigma; g1 *= sigma; g2 *= sigma;
                         ul = rng_particle_uniform(id, step, (uint32_t)nl);
                     }
