@@ -478,6 +478,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
 
                     // gas-phase fast path: nobody in range of the proposal -> all pair and site sums are exactly 0
                     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+                    double le = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
                     unsigned in_new = 0;
                     const bool work = __any_sync(FULL, hits_new != 0) || near;
                     if (work) {
@@ -491,6 +492,9 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                                 in_new |= 1u << k;
                             }
                         }
+                        // a lane with exactly one partner (the usual case) holds that pair's terms in e, fx, fy, fz:
+                        // keep them for the partner's cache update instead of evaluating the pair again
+                        le = e; lx = fx; ly = fy; lz = fz;
                         if (near) add_sites(b, s, lane, MMpad, qx, qy, dzw, e, fx, fy, fz);
                         // Sum over the warp.  Usually one or two lanes hold a partner: their four partial sums are
                         // fetched with independent shuffles (one shuffle latency) instead of the five dependent
@@ -526,12 +530,13 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                         int nbn = 0;
                         if (work) {
                             unsigned hn = in_new;
+                            const bool single = __popc(in_new) == 1 && !(near && lane < MM);   // le.. are that one pair's terms
                             while (hn) {
                                 const int k = __ffs(hn) - 1;
                                 hn &= hn - 1;
                                 const int j = particle_of(k);
-                                double et, hx, hy, hz;
-                                pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz);
+                                double et = le, hx = lx, hy = ly, hz = lz;
+                                if (!single) pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz);
                                 s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
                                 s.nb[j] += 1;
                                 touched |= (k == 0);

@@ -1,4 +1,5 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -4
-python bench.py --steps 5 --no-cpu-baseline 2>/dev/null | python -c "
+for lib in "" build/variants/libsmcb200_reg152.so build/variants/libsmcb200_reg144.so; do
+  SMCB200_LIB=$lib python bench.py --no-cpu-baseline --no-e2e --steps 3 --thermalise 0 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('batched', d['value'], d['kernel_ms_per_step'], d['gather_ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['thermalised']['kernel_ms_per_step'], d['allparticle_kernel']['kernel_ms_per_step'], d['allparticle_kernel']['roofline_frac'])"
+d=json.loads(sys.stdin.read()); print('$lib', d['value'], d['kernel_ms_per_step'], d['roofline']['frac'])"
+done
