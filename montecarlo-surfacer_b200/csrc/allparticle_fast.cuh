@@ -233,7 +233,6 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
     extern __shared__ double sm[];
     StepSmem s;
     s.carve(sm, Npad, N, HALF);
-    __shared__ int s_accept;
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, d.step_scale);
     const ScreenConsts sc = make_screen(b);
@@ -257,7 +256,13 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
     // stage one configuration: exact + box-unit single precision; pad slots far away
     auto stage = [&](int j, double X, double Y, double Z) {
         s.x[j] = X; s.y[j] = Y; s.z[j] = Z;
-        s.fx[j] = (float)(X * b.invL); s.fy[j] = (float)(Y * b.invL); s.fz[j] = (float)(Z * b.invL);
+        const float fx = (float)(X * b.invL), fy = (float)(Y * b.invL), fz = (float)(Z * b.invL);
+        s.fx[j] = fx; s.fy[j] = fy; s.fz[j] = fz;
+        if (HALF) {            // the circular copies (A[m] = particle m mod N, B[m] = A[m+1]) and cleared backward words
+            for (int m = j; m < s.NE; m += N) { s.circ(0, 0)[m] = fx; s.circ(1, 0)[m] = fy; s.circ(2, 0)[m] = fz; }
+            for (int m = (j == 0 ? N - 1 : j - 1); m < s.NE; m += N) { s.circ(0, 1)[m] = fx; s.circ(1, 1)[m] = fy; s.circ(2, 1)[m] = fz; }
+            for (int c = 0; c < s.NW; c++) s.bw[j * s.NW + c] = 0u;
+        }
     };
     auto stage_pad = [&]() {
         for (int j = N + tid; j < Npad; j += T_) { s.x[j] = 0.0; s.y[j] = 0.0; s.z[j] = 0.0; s.fx[j] = 0.f; s.fy[j] = 0.f; s.fz[j] = 3.0e18f; }
@@ -265,16 +270,7 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
     // forces / energies of this block's molecules at the staged configuration; returns the MH partial sums
     auto evaluate_owned = [&](double *Fout, const double *Fold, bool with_mh, double (&t)[3]) {
         t[0] = t[1] = t[2] = 0.0;
-        if (HALF) {
-            // circular screen-precision copies (two alignments) and cleared backward words, then phase 1
-            for (int m = tid; m < s.NE; m += T_) {
-                int j0 = m; while (j0 >= N) j0 -= N;
-                int j1 = m + 1; while (j1 >= N) j1 -= N;
-                s.circ(0, 0)[m] = s.fx[j0]; s.circ(1, 0)[m] = s.fy[j0]; s.circ(2, 0)[m] = s.fz[j0];
-                s.circ(0, 1)[m] = s.fx[j1]; s.circ(1, 1)[m] = s.fy[j1]; s.circ(2, 1)[m] = s.fz[j1];
-            }
-            for (int m = tid; m < N * s.NW; m += T_) s.bw[m] = 0u;
-            __syncthreads();
+        if (HALF) {            // phase 1 (the caller's barrier after staging covers the circular copies and bw = 0)
             for (int i = tid; i < N; i += T_) half_shell_screen<PZ>(sc, s, N, i, s.fx[i], s.fy[i], s.fz[i]);
             __syncthreads();
         }
@@ -349,19 +345,17 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
         double t[3];                       // U', sum d.(F'+F), sum |F'|^2-|F|^2
         evaluate_owned(Fn, Fc, true, t);
         const double lnap = -((t[0] - U) + t[1] / 2.0 + t[2] * b.A / (4.0 * b.T)) / b.T;
-        if (tid == 0) {
-            double uu;
-            if (FED) uu = a.u[sci];
-            else { uint32_t o; rng_step_scalars(id, step, o, uu); }
-            const int acc = uu < exp(lnap);
-            s_accept = acc;
-            if (part == 0) {
-                if (a.lnap) a.lnap[sci] = lnap;
-                if (a.accepted) a.accepted[sci] = (unsigned char)acc;
-            }
+        // every thread of every block of the chain holds the same sums and draws the same Philox number: the
+        // decision needs no broadcast and no barrier
+        double uu;
+        if (FED) uu = a.u[sci];
+        else { uint32_t o; rng_step_scalars(id, step, o, uu); }
+        const bool acc = uu < exp(lnap);
+        if (tid == 0 && part == 0) {
+            if (a.lnap) a.lnap[sci] = lnap;
+            if (a.accepted) a.accepted[sci] = (unsigned char)acc;
         }
-        __syncthreads();
-        if (s_accept) {
+        if (acc) {
             for (int i = part + CL * tid; i < N; i += CL * T_) { P[i] = s.x[i]; P[Npad + i] = s.y[i]; P[2 * Npad + i] = s.z[i]; }
             double *tp = Fc; Fc = Fn; Fn = tp;
             U = t[0];

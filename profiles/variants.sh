@@ -1,5 +1,4 @@
-for lib in "" build/variants/libsmcb200_reg152.so build/variants/libsmcb200_reg144.so; do
-  SMCB200_LIB=$lib python bench.py --no-cpu-baseline --no-e2e --steps 3 --thermalise 0 2>/dev/null | python -c "
+python -m pytest tests/test_gpu_allparticle.py tests/test_gpu_equilibrium.py tests/test_gpu_observables.py -m gpu -q -x 2>&1 | tail -4
+python bench.py --steps 3 --no-cpu-baseline --no-e2e --thermalise 0 --kernel allparticle 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('$lib', d['value'], d['kernel_ms_per_step'], d['roofline']['frac'])"
-done
+d=json.loads(sys.stdin.read()); print('allparticle', d['value'], d['kernel_ms_per_step'], d['roofline']['frac'])"
