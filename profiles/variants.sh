@@ -1,4 +1,6 @@
-python -m pytest tests/test_gpu_allparticle.py tests/test_gpu_equilibrium.py tests/test_gpu_observables.py -m gpu -q -x 2>&1 | tail -4
-python bench.py --steps 3 --no-cpu-baseline --no-e2e --thermalise 0 --kernel allparticle 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('allparticle', d['value'], d['kernel_ms_per_step'], d['roofline']['frac'])"
+python -m pytest tests -m gpu -q 2>&1 | tail -3
+python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; tail -2 gpurun_out/final_bench.err
+python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/final_ref.json 2>/dev/null
+python bench.py --workload largeN --steps 3 --sweeps-per-step 10 --no-cpu-baseline > gpurun_out/final_largeN.json 2>/dev/null
+python bench.py --workload grid --steps 2 --no-cpu-baseline > gpurun_out/final_grid.json 2>/dev/null
+wc -c gpurun_out/final_*.json
