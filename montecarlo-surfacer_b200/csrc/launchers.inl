@@ -55,7 +55,8 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
     else     k_sweep<K, true, false><<<d.C, 32, smem, st>>>(d, a);
 #else
     const int MMpad = (d.M * d.M + 3) & ~3;
-    const size_t smem = ChainSmem::bytes(32 * K, MMpad);
+    size_t smem = ChainSmem::bytes(32 * K, MMpad);
+    if (const char *env = getenv("SMCB_SWEEP_SMEM_PAD")) smem += (size_t)atoi(env);     // occupancy experiments (profiles/)
     cudaError_t err;
     if (fed) {
         auto kern = k_sweep_cached<K, true>;
