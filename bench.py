@@ -219,7 +219,7 @@ def main():
     os.dup2(2, 1)
     import torch
     smcb = importlib.import_module("montecarlo-surfacer_b200")
-    from oracle_bindings import GOLDEN_W_M3
+    GOLDEN_W_M3 = smcb.REFERENCE_WALL_M3          # main.c's wall table; nothing under oracle/ is touched by this arm
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

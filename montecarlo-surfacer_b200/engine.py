@@ -14,6 +14,20 @@ WALL, PERIODIC_Z = 1, 2
 A0_DEFAULT = 5.960464477539063e-9   # SMC.h:32
 B0_DEFAULT = 2.44140625e-5          # SMC.h:33
 
+# The wall table main.c builds: initializeWalls(1.6, 0.0, 3.0, 0.5, W, f) after its srand(42), M = 3 (main.c:74-87,
+# SMC.c:475-501; values from SURVEY.md App. D, glibc rand).  W[2m] = a, W[2m+1] = b, m = i*M + j.
+REFERENCE_WALL_M3 = np.array([
+    962.2264072645321, 57.35316319850277,
+    874.39446992695275, 52.11797177356199,
+    857.36680597299653, 51.103043912231705,
+    1024.1964124687327, 61.046863345428257,
+    925.40789594507817, 55.158608910148025,
+    913.63518965684239, 54.456900933792724,
+    848.90539177252572, 50.598704324515197,
+    992.35137245273086, 59.148751047416368,
+    844.42493013196849, 50.331648000000015,
+])
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
