@@ -1,3 +1,1 @@
-for pad in 0 10000 23000 42000; do
-echo "pad $pad"; SMCB_SWEEP_SMEM_PAD=$pad python profiles/fastpath_probe.py
-done
+python -m pytest tests/test_gpu_allparticle.py -m gpu -q -x 2>&1 | tail -5

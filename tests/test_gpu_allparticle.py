@@ -18,7 +18,8 @@ def orc():
 
 
 @pytest.mark.parametrize("mode", [smcb.STRICT, smcb.FAST])
-@pytest.mark.parametrize("N,A,nsteps", [(108, 2e-4, 30), (256, 1e-4, 12), (32, 1e-3, 60)])
+@pytest.mark.parametrize("N,A,nsteps", [(108, 2e-4, 30), (256, 1e-4, 12), (32, 1e-3, 60), (101, 2e-4, 20), (33, 1e-3, 40),
+                                        (500, 5e-5, 8)])
 def test_allparticle_fed_matches_oracle(orc, mode, N, A, nsteps):
     M, T = 3, 1.1
     L, Lz = geom(N)
