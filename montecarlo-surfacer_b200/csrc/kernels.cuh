@@ -3,9 +3,11 @@
 //
 //   k_evaluate      static per-particle / per-chain energies, forces, virials
 //                   (reference rows a2-a10: SMC.c:557-895)
-//   k_sweep         the reference's live move, oneParticleMoves (SMC.c:278-351):
-//                   N sequential single-particle Smart-MC trials, one WARP per
-//                   chain, positions register-resident
+//   k_sweep         the reference's live move, oneParticleMoves (SMC.c:278-351), in
+//                   the reference's arithmetic (STRICT, bit-exact parity): N sequential
+//                   single-particle Smart-MC trials, one WARP per chain, positions
+//                   register-resident.  The FAST sweep is k_sweep_cached (sweep_cached.cuh),
+//                   the FAST all-particle step and evaluation are in allparticle_fast.cuh
 //   k_allparticle   the all-particle Smart-MC step (north-star kernel B), one CTA
 //                   per chain, proposal positions tiled in shared memory
 //   k_gather        localDensityAndMobility (SMC.c:912-927) + histograms/moments
@@ -151,34 +153,7 @@ __global__ void k_evaluate(DevChains d, EvalOut o)
 // added one by one in ascending particle index (k-major, lane-minor = l
 // ascending), all lanes keeping identical accumulators.  The surface terms
 // follow in the reference's order (flat wall, then sites m ascending).
-// ---- FAST-path building blocks of the sweep kernel ---------------------------
-#ifndef SMCB_RINT_MODE
-#define SMCB_RINT_MODE 0
-#endif
-// round-to-nearest-even of a small number: FRND.F64 (XU pipe) or the 2^52+2^51
-// add/subtract trick (two DADDs on the FP64 pipe); both are exact.
-__device__ __forceinline__ double rint_xu(double s) { return rint(s); }
-__device__ __forceinline__ double rint_magic(double s)
-{
-    return __dsub_rn(__dadd_rn(s, 6755399441055744.0), 6755399441055744.0);
-}
-__device__ __forceinline__ double wrap_unit_x(double s)
-{
-#if SMCB_RINT_MODE == 1
-    return s - rint_magic(s);
-#else
-    return s - rint_xu(s);
-#endif
-}
-__device__ __forceinline__ double wrap_unit_y(double s)
-{
-#if SMCB_RINT_MODE == 0
-    return s - rint_xu(s);
-#else
-    return s - rint_magic(s);
-#endif
-}
-
+// ---- shared FAST-path helpers (used by sweep_cached.cuh and allparticle_fast.cuh) ----------------
 // 1/x for a positive normal x to ~1 ulp without the slow-path call of the IEEE
 // division: MUFU.RCP64H seed (rcp.approx.ftz.f64, 2^-23) + two Newton steps.
 __device__ __forceinline__ double fast_rcp(double x)
@@ -212,106 +187,6 @@ __device__ __forceinline__ void warp_sum4(int lane, double &a, double &b, double
     b = __shfl_sync(FULL, v, 8);
     c = __shfl_sync(FULL, v, 16);
     d = __shfl_sync(FULL, v, 24);
-}
-
-// per-lane surface site (lane m < M*M owns site m = i*M + j at (i*dw, j*dw), SMC.c:745-750)
-struct LaneSite {
-    double sx, sy, ca, cb;
-    bool on;
-};
-
-// FAST pass of the sweep kernel.  xs/ys/zs hold the lane's particles in units of L
-// (x/L, y/L, z/L): the minimum image is then s - rint(s) and the squared distance in
-// box units is compared with rc2/L^2, 9 FP64-pipe instructions per pair.  Phase 1 walks
-// all K slots and only records which are inside the cutoff; phase 2 (rare in the gas)
-// re-reads each hit's unscaled position from the shared-memory mirror and adds its 12-6
-// terms exactly as k_evaluate's FAST path does.  okmask: bit k set when slot k is a real particle
-// other than the trial particle.
-template <int K>
-__device__ __forceinline__ void sweep_pass_fast(const Box &b, const LaneSite &site, const double *__restrict__ W,
-                                                int lane, unsigned okmask, double px, double py, double pz,
-                                                const double (&xs)[K], const double (&ys)[K], const double (&zs)[K],
-                                                const double *smx, const double *smy, const double *smz,
-                                                double rc2s, double zperiod_s, double inv_zperiod_s,
-                                                double &U, double &Fx, double &Fy, double &Fz, unsigned long long &cnt)
-{
-    const double psx = px * b.invL, psy = py * b.invL, psz = pz * b.invL;
-    unsigned hits = 0;
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const double sx = wrap_unit_x(psx - xs[k]);
-        const double sy = wrap_unit_y(psy - ys[k]);
-        double sz = psz - zs[k];
-        if (b.pz) sz = fma(-zperiod_s, rint(sz * inv_zperiod_s), sz);
-        const double r2s = fma(sz, sz, fma(sy, sy, sx * sx));
-        if (r2s < rc2s) hits |= 1u << k;
-    }
-    hits &= okmask;
-    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-    while (hits) {                                     // divergent, rare in the gas phase
-        const int k = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const int j = lane + 32 * k;                    // unscaled neighbour from the shared-memory mirror
-        double dx, dy, dz;
-        const double r2 = pair_sep<false>(b, px, py, pz, smx[j], smy[j], smz[j], dx, dy, dz);
-        if (r2 < b.rc2) {
-            const double i2 = fast_rcp(r2);
-            const double i6 = i2 * i2 * i2;
-            e += fma(i6, i6, -i6);
-            const double g = i2 * i6 * fma(48.0, i6, -24.0);
-            fx = fma(g, dx, fx);
-            fy = fma(g, dy, fy);
-            fz = fma(g, dz, fz);
-            cnt++;
-        }
-    }
-    double dzw = 0.0;
-    if (b.wall) {
-        dzw = wall_dz<false>(b, pz);
-        if (dzw * dzw < b.rc2) {                       // warp-uniform: no site can be in range otherwise
-            if (site.on) {
-                const double dx = min_image<false>(px - site.sx, b.L, b.invL);
-                const double dy = min_image<false>(py - site.sy, b.L, b.invL);
-                const double r2 = fma(dzw, dzw, fma(dy, dy, dx * dx));
-                if (r2 < b.rc2) {
-                    const double i2 = fast_rcp(r2);
-                    const double i6 = i2 * i2 * i2;
-                    const double a6 = site.ca * i6;
-                    e += fma(a6, i6, -site.cb * i6);
-                    const double g = i2 * i6 * fma(48.0, a6, -24.0 * site.cb);
-                    fx = fma(g, dx, fx);
-                    fy = fma(g, dy, fy);
-                    fz = fma(g, dzw, fz);
-                }
-            }
-            const int MM = b.M * b.M;
-            const double dw = b.L / b.M;
-            for (int m = lane + 32; m < MM; m += 32) {   // M > 5 only
-                const int i = m / b.M, j = m - i * b.M;
-                const double dx = min_image<false>(px - i * dw, b.L, b.invL);
-                const double dy = min_image<false>(py - j * dw, b.L, b.invL);
-                const double r2 = fma(dzw, dzw, fma(dy, dy, dx * dx));
-                if (r2 < b.rc2) {
-                    double et, g;
-                    lj_terms<false, false>(r2, W[2 * m], W[2 * m + 1], et, g);
-                    e += et;
-                    fx = fma(g, dx, fx);
-                    fy = fma(g, dy, fy);
-                    fz = fma(g, dzw, fz);
-                }
-            }
-        }
-    }
-    warp_sum4(lane, e, fx, fy, fz);
-    if (b.wall) {                                       // flat wall: same on every lane, no cutoff
-        const double i2 = fast_rcp(dzw * dzw);
-        const double i6 = i2 * i2 * i2;
-        const double a6 = b.a0 * i6;
-        e += fma(a6, i6, -b.b0 * i6);
-        fz = fma(i2 * i6 * fma(48.0, a6, -24.0 * b.b0), dzw, fz);
-    }
-    U = 4.0 * e;
-    Fx = fx; Fy = fy; Fz = fz;
 }
 
 template <int K, bool STRICT>
@@ -456,18 +331,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
         if (in) validmask |= 1u << k;
     }
     __syncwarp();
-    LaneSite site;
-    site.on = b.wall && lane < d.M * d.M;
-    {
-        const int si = lane / d.M, sj = lane - si * d.M;
-        const double dw = b.L / d.M;
-        site.sx = si * dw; site.sy = sj * dw;
-        site.ca = site.on ? W[2 * lane] : 0.0;
-        site.cb = site.on ? W[2 * lane + 1] : 0.0;
-    }
-    const double rc2s = b.rc2 * b.invL * b.invL * (1.0 + 1e-12);   // phase-1 screen, exact test in phase 2
-    const double zperiod_s = b.Lz * b.invL, inv_zperiod_s = b.L * b.invLz;
-
+    static_assert(STRICT, "k_sweep is the parity kernel; the FAST sweep is k_sweep_cached (sweep_cached.cuh)");
     const double AoT = b.A / b.T;
     const double sigma = sqrt(2.0 * b.A);            // vecBoxMuller(sqrt(2.0*A), ...)  SMC.c:284
     double E = d.E[chain];
@@ -515,10 +379,8 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
                 const int owner = n & 31, slot = n >> 5;
                 const double px = sx[n], py = sy[n], pz = sz[n];
 
-                const unsigned okmask = validmask & ~((lane == owner) ? (1u << slot) : 0u);
                 double Um, Fmx, Fmy, Fmz;              // SMC.c:300-304
-                if (STRICT) sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, px, py, pz, x, y, z, Um, Fmx, Fmy, Fmz, cnt);
-                else sweep_pass_fast<K>(b, site, W, lane, okmask, px, py, pz, x, y, z, sx, sy, sz, rc2s, zperiod_s, inv_zperiod_s, Um, Fmx, Fmy, Fmz, cnt);
+                sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, px, py, pz, x, y, z, Um, Fmx, Fmy, Fmz, cnt);
 
                 double dX, dY, dZ;                      // SMC.c:307-309
                 if (STRICT) {
@@ -536,8 +398,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
                 if (b.pz) qz = min_image<STRICT>(qz, b.Lz, b.invLz);
 
                 double Un, Fnx, Fny, Fnz;              // SMC.c:319-321
-                if (STRICT) sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, qx, qy, qz, x, y, z, Un, Fnx, Fny, Fnz, cnt);
-                else sweep_pass_fast<K>(b, site, W, lane, okmask, qx, qy, qz, x, y, z, sx, sy, sz, rc2s, zperiod_s, inv_zperiod_s, Un, Fnx, Fny, Fnz, cnt);
+                sweep_pass<K, STRICT>(b, W, N, lane, owner, slot, qx, qy, qz, x, y, z, Un, Fnx, Fny, Fnz, cnt);
 
                 double ap;                              // SMC.c:326-329
                 if (STRICT) {

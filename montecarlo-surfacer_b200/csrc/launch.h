@@ -7,12 +7,12 @@ namespace smcb {
 // kernels_fast.cu (FMA contraction on) and kernels_strict.cu (--fmad=false)
 // each define one set; `strict` picks the set at run time in engine.cu.
 #define SMCB_DECLARE_LAUNCHERS(SUFFIX)                                                              \
-    cudaError_t launch_evaluate_##SUFFIX(const DevChains &d, const EvalOut &o, cudaStream_t st);    \
     cudaError_t launch_sweep_##SUFFIX(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st); \
     cudaError_t launch_allparticle_##SUFFIX(bool fed, const DevChains &d, const StepArgs &a, cudaStream_t st);
 
 SMCB_DECLARE_LAUNCHERS(fast)
 SMCB_DECLARE_LAUNCHERS(strict)
+cudaError_t launch_evaluate_strict(const DevChains &d, const EvalOut &o, cudaStream_t st);   // FAST: launch_evaluate_fast_screened
 
 int evaluate_fast_parts(const DevChains &d);
 cudaError_t launch_evaluate_fast_screened(const DevChains &d, const EvalOut &o, int parts, double *partials, unsigned *tickets, cudaStream_t st);

@@ -36,6 +36,7 @@ cudaError_t launch_evaluate_fast_screened(const DevChains &d, const EvalOut &o, 
 }
 #endif
 
+#if SMCB_TU_IS_STRICT
 cudaError_t SMCB_CAT(launch_evaluate_, SMCB_TU_SUFFIX)(const DevChains &d, const EvalOut &o, cudaStream_t st)
 {
     const size_t smem = (size_t)(3 * d.Npad + 8 * 32) * sizeof(double);
@@ -45,6 +46,7 @@ cudaError_t SMCB_CAT(launch_evaluate_, SMCB_TU_SUFFIX)(const DevChains &d, const
     kern<<<d.C, eval_threads(d.N), smem, st>>>(d, o);
     return cudaGetLastError();
 }
+#endif
 
 template <int K>
 static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
