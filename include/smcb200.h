@@ -42,7 +42,9 @@ extern "C" {
                                 wrapped in z (SMC_noMPI_noWall.c:470-475); no reference in SMC.c */
 
 /* arithmetic variants of the kernels */
-#define SMCB_FAST    0  /* fused FMA formulation, one reciprocal per pair, tree reductions        */
+#define SMCB_FAST    0  /* fused FMA formulation, one reciprocal per pair, tree reductions; the cutoff
+                           test runs as a conservative packed-FP32 screen and every pair inside the
+                           cutoff is evaluated in FP64 (same sums as an all-FP64 loop); <= 1e-12 rel.  */
 #define SMCB_STRICT  1  /* the reference's IEEE operation order (no FMA, true divisions, sums in
                            the reference's particle order): bit-identical per-particle results   */
 
@@ -110,7 +112,8 @@ int smcb_evaluate(smcb_engine *e, int mode,
                   double *U_lj, double *U_wall, double *vir_lj, double *vir_wall_ref);
 
 /* ---- the sweep (row a1: oneParticleMoves, SMC.c:278-351) -----------------
- * nsweeps sweeps of N sequential single-particle Smart-MC trials per chain.
+ * nsweeps sweeps of N sequential single-particle Smart-MC trials per chain
+ * (N <= 512: one warp per chain; larger N: use the all-particle step).
  * Running energy (+= Un-Um on acceptance, SMC.c:341) and acceptance counts
  * accumulate in the chain state (smcb_get_chain_state).
  *
