@@ -189,6 +189,14 @@ int smcb_obs_get(smcb_engine *e, uint64_t *counters, double *moments);          
  * the block to / from caller-provided DEVICE buffers (same layout). */
 int smcb_obs_export_device(smcb_engine *e, void *counters_dev, void *moments_dev);
 int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void *moments_dev);
+/* One process driving several GPUs (one engine per GPU): sum the observable blocks of the n engines
+ * in place with NCCL over NVLink - one ncclAllReduce(ncclUint64) of the counters and one
+ * ncclAllReduce(ncclFloat64) of the moments, the only collective of the path - so that every engine
+ * ends up holding the job's totals.  All engines must have the same observable layout.  NCCL is
+ * loaded at run time (dlopen "libnccl.so.2"); SMCB_ERR_STATE if it is not available.  With one
+ * process per GPU (torch.distributed, MPI) use smcb_obs_export_device / _import_device and the
+ * launcher's own all-reduce instead. */
+int smcb_obs_allreduce(smcb_engine **engines, int n);
 /* per-chain Rbin (voxel of each particle at the last gather), nchains*N ints */
 int smcb_get_rbin(smcb_engine *e, int32_t *rbin);
 int smcb_set_rbin(smcb_engine *e, const int32_t *rbin);

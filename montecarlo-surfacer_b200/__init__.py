@@ -8,11 +8,11 @@ Engine does not.
 """
 from .engine import (FAST, STRICT, WALL, PERIODIC_Z, ChainParams, Engine, ObsLayout, SmcbError,
                      default_params, lib_path, load_library, exported_symbols, header_symbols,
-                     obs_layout_host, unpack_obs, REFERENCE_WALL_M3)
+                     obs_layout_host, unpack_obs, obs_allreduce, REFERENCE_WALL_M3)
 from .shard import (Shard, shard_chains, grid_points, grid_chain_params, allreduce_observables,
                     max_over_ranks)
 
 __all__ = ["FAST", "STRICT", "WALL", "PERIODIC_Z", "ChainParams", "Engine", "ObsLayout", "SmcbError",
            "default_params", "lib_path", "load_library", "exported_symbols", "header_symbols",
-           "obs_layout_host", "unpack_obs", "REFERENCE_WALL_M3", "Shard", "shard_chains", "grid_points", "grid_chain_params",
+           "obs_layout_host", "unpack_obs", "obs_allreduce", "REFERENCE_WALL_M3", "Shard", "shard_chains", "grid_points", "grid_chain_params",
            "allreduce_observables", "max_over_ranks"]

@@ -5,6 +5,8 @@
 // chain, SMC.h:84); the AoS<->SoA transposes run on the device.  There is no CPU
 // fallback anywhere in this file: every entry point either launches the sm_100a
 // kernels or returns an error.
+#include <dlfcn.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -665,6 +667,78 @@ int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void 
     return SMCB_OK;
 }
 
+}  // extern "C"
+
+// ---- single-process multi-GPU all-reduce of the observable blocks (NCCL loaded at run time) ----------
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(dlsym(lib, "ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(lib, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+std::vector<int> g_nccl_devs;          // device list the cached communicators were built for
+std::vector<void *> g_nccl_comms;
+constexpr int kNcclSum = 0, kNcclUint64 = 5, kNcclFloat64 = 8;     // nccl.h: ncclSum, ncclUint64, ncclFloat64
+}  // namespace
+
+extern "C" int smcb_obs_allreduce(smcb_engine **engines, int n)
+{
+    if (!engines || n <= 0) return fail(SMCB_ERR_ARG, "need n > 0 engines");
+    for (int i = 0; i < n; i++) {
+        if (!engines[i] || !engines[i]->counters.p) return fail(SMCB_ERR_STATE, "engine %d has no observable block", i);
+        if (engines[i]->u64_per_group() * engines[i]->ngroups != engines[0]->u64_per_group() * engines[0]->ngroups)
+            return fail(SMCB_ERR_ARG, "engine %d has a different observable layout", i);
+        for (int j = 0; j < i; j++)
+            if (engines[j]->device == engines[i]->device) return fail(SMCB_ERR_ARG, "engines %d and %d share GPU %d", j, i, engines[i]->device);
+    }
+    if (n == 1) return SMCB_OK;
+    if (!g_nccl.load()) return fail(SMCB_ERR_STATE, "NCCL not available (dlopen libnccl.so.2: %s)", dlerror());
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) devs[i] = engines[i]->device;
+    if (devs != g_nccl_devs) {
+        for (void *c : g_nccl_comms) g_nccl.CommDestroy(c);
+        g_nccl_comms.assign(n, nullptr);
+        const int rc = g_nccl.CommInitAll(g_nccl_comms.data(), n, devs.data());
+        if (rc != 0) { g_nccl_comms.clear(); g_nccl_devs.clear(); return fail(SMCB_ERR_CUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString(rc)); }
+        g_nccl_devs = devs;
+    }
+    const size_t ncnt = engines[0]->u64_per_group() * engines[0]->ngroups, nmom = engines[0]->f64_per_group() * engines[0]->ngroups;
+    int rc = g_nccl.GroupStart();
+    for (int i = 0; i < n && rc == 0; i++) {
+        smcb_engine *e = engines[i];
+        CK(cudaSetDevice(e->device));
+        rc = g_nccl.AllReduce(e->counters.p, e->counters.p, ncnt, kNcclUint64, kNcclSum, g_nccl_comms[i], e->stream);
+        if (rc == 0) rc = g_nccl.AllReduce(e->moments.p, e->moments.p, nmom, kNcclFloat64, kNcclSum, g_nccl_comms[i], e->stream);
+    }
+    const int rc2 = g_nccl.GroupEnd();
+    if (rc != 0 || rc2 != 0) return fail(SMCB_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(rc != 0 ? rc : rc2));
+    for (int i = 0; i < n; i++) {
+        CK(cudaSetDevice(engines[i]->device));
+        CK(cudaStreamSynchronize(engines[i]->stream));
+    }
+    return SMCB_OK;
+}
+
+extern "C" {
 int smcb_get_rbin(smcb_engine *e, int32_t *rbin)
 {
     int rc = check(e);

@@ -376,6 +376,17 @@ class Engine:
         return self.lib.smcb_stream(self._h)
 
 
+def obs_allreduce(engines):
+    """smcb_obs_allreduce: sum the observable blocks of several engines of THIS process (one per GPU) with NCCL"""
+    lib = load_library()
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    lib.smcb_obs_allreduce.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.smcb_obs_allreduce.restype = C.c_int
+    rc = lib.smcb_obs_allreduce(arr, len(engines))
+    if rc != 0:
+        raise SmcbError(f"smcb error {rc}: {lib.smcb_last_error().decode()}")
+
+
 def obs_layout_host(ngroups, nebins=64, e_lo=-8.0, e_hi=2.0):
     """the layout smcb_obs_layout_get reports, computed on the host (no engine needed): per group
     D[33^3] Mu[33^3] zprof[33] ehist[nebins] nsamples | sumE sumE2 sumP sumP2 sumAcc"""

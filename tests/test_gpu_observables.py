@@ -147,3 +147,36 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
         eng.set_params(par, GOLDEN_W_M3)
         with pytest.raises(smcb.SmcbError):
             eng.checkpoint_load(ck)
+
+
+def test_obs_allreduce_single_process_two_gpus():
+    """smcb_obs_allreduce: one process, one engine per GPU, NCCL all-reduce of the observable blocks - the
+    path's only collective, from C.  Needs two GPUs (gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    N, M = 108, 3
+    L, Lz = geom(N)
+    orc = Oracle()
+    R0, _ = orc.initialize_box(L, Lz, N)
+    engines, blocks = [], []
+    try:
+        for dev in range(2):
+            eng = smcb.Engine(8, N, M, device=dev)
+            eng.set_params(smcb.default_params(L=L, Lz=Lz), GOLDEN_W_M3)
+            eng.broadcast_positions(R0)
+            eng.set_rng(5, 8 * dev, 0)
+            eng.sweep(6, smcb.FAST)
+            eng.gather()
+            engines.append(eng)
+            blocks.append(eng.obs_get()[0])
+        smcb.obs_allreduce(engines)
+        for eng in engines:
+            o = eng.obs_get()[0]
+            for k in ("D", "Mu", "zprof", "ehist"):
+                np.testing.assert_array_equal(o[k], blocks[0][k] + blocks[1][k])
+            assert o["nsamples"] == 16 and o["D"].sum() == 16 * N
+            assert abs(o["sumE"] - (blocks[0]["sumE"] + blocks[1]["sumE"])) <= 1e-12 * abs(o["sumE"])
+    finally:
+        for eng in engines:
+            eng.close()
