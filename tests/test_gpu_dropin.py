@@ -163,3 +163,21 @@ def test_reference_main_unchanged_runs_on_the_dropin(tmp_path):
     # second run restarts from last_state (main.c:98-109)
     r2 = subprocess.run([exe, "10", "40", "4", "1.1"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     assert r2.returncode == 0 and "Using previously saved particle configuration" in r2.stdout
+
+
+def test_batched_c_driver_runs(tmp_path):
+    """examples/batched_driver.c: a plain C program on the batched C ABI (one engine per visible GPU,
+    thermalisation, sweeps + gathers, smcb_obs_allreduce) built against the drop-in's SMC.h"""
+    exe = os.path.join(BUILD, "batched_driver_N108")
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} missing: run `make -C tests/dropin`")
+    r = subprocess.run([exe, "64", "40", "120", "40", "1.1", "2"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    out = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines() if " " in line)
+    head = r.stdout.splitlines()[0].split()
+    ngpu, chains, gathers, samples = int(head[1]), int(head[3]), int(head[7]), int(head[9])
+    assert chains == 64 * ngpu and gathers == 3 and samples == chains * gathers
+    mass, expected = int(out["mass"].split()[0]), int(out["mass"].split()[2])
+    assert mass == expected == samples * 108
+    acc = float(out["mean_E"].split()[4])
+    assert 0.8 < acc <= 1.0
