@@ -58,6 +58,10 @@ def parse():
                          "16 T x 4 Lz x 4 wall-strength grid x 256 replicas, sharded over the GPUs, one observable group per "
                          "grid point (configs[3]); largeN: 256 chains x N=4096 in total, sharded over the GPUs (configs[4], "
                          "all-particle kernel with thread-block clusters)")
+    ap.add_argument("--start", default="lattice", choices=["lattice", "droplet"],
+                    help="lattice: initializeBox's dilute fcc lattice (the reference's start); droplet: all molecules condensed "
+                         "on the lower wall (jittered simple-cubic block, spacing 1.12: ~80 partners inside the cutoff each) - "
+                         "the state long reference runs end in")
     ap.add_argument("--thermalise", type=int, default=2000,
                     help="sweeps with 2A (sMC's thermalisation, SMC.c:110-125) before the extra 'thermalised' timing leg; 0 = skip")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
@@ -249,6 +253,8 @@ def main():
         grid = (shard, temps, lzs, walls, total_grid)
     mode = smcb.STRICT if args.mode == "strict" else smcb.FAST
     A = TEMP if args.kernel == "sweep" else (2e-4 if N <= 256 else 2e-6)
+    if args.start == "droplet" and args.kernel == "sweep":
+        A = 0.02                                     # A = T moves 1.5 sigma per trial: nothing is accepted inside a liquid
 
     # start lattice of initializeBox(33, 240, 256) (SMC.c:413-465): 4x4x4 fcc cells, a = 8.25, shifted a/4
     # (N=4096: 16x16x4 cells, a = 33/16 - the reference's own generator is invalid there)
@@ -261,6 +267,16 @@ def main():
     X[:, :2] -= L_BOX * np.rint(X[:, :2] / L_BOX)
     X[:, 2] -= Pz * np.rint(X[:, 2] / Pz)
     R0 = X.reshape(-1)
+    if args.start == "droplet":
+        nzl = 4 if N <= 512 else 8
+        nxy = int(np.ceil(np.sqrt(N / nzl)))
+        g = np.array([(i, j, k) for k in range(nzl) for i in range(nxy) for j in range(nxy)], dtype=float)[:N]
+        g[:, 0] = (g[:, 0] - nxy / 2) * 1.12
+        g[:, 1] = (g[:, 1] - nxy / 2) * 1.12
+        g[:, 2] = -LZ_BOX / 2 + 0.95 + g[:, 2] * 1.12
+        rs = np.random.default_rng(7)
+        g += (rs.random(g.shape) * 2 - 1) * 0.05
+        R0 = g[rs.permutation(N)].reshape(-1)
 
     eng = smcb.Engine(Cn, N, M_SITES, device=local)
     if grid:
@@ -385,7 +401,7 @@ def main():
 
     # ---- extra legs (reported beside the headline, same JSON line) -----------------------------
     extra = {}
-    if args.workload == "batched" and args.kernel == "sweep" and mode == smcb.FAST:
+    if args.workload == "batched" and args.kernel == "sweep" and mode == smcb.FAST and args.start == "lattice":
         if args.thermalise > 0:
             # sMC's thermalisation (2A, SMC.c:110-125) so molecules reach the wall and partners become common
             eng.set_step_scale(2.0)
@@ -426,7 +442,7 @@ def main():
                                     if grid else f"{int(total_largeN)} chains x N={N} with wall in total (BASELINE configs[4]), {Cn} on this rank")
                                    + f", {args.kernel} kernel, {args.mode}",
                        "chains_per_gpu": Cn, "N": N, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": A,
-                       "sweeps_per_step": S, "start": "initializeBox fcc lattice + warm-up steps",
+                       "sweeps_per_step": S, "start": ("initializeBox fcc lattice" if args.start == "lattice" else "condensed droplet on the wall") + " + warm-up steps",
                        "l2": "flushed between timed steps (256 MB write)", "rng": "Philox4x32-10",
                        "parallelism": f"chains sharded x{world}, NCCL all-reduce of the observable block only"},
             "kernel_ms_per_step": main["kernel_ms_per_step"], "gather_ms_per_step": main["gather_ms_per_step"],
