@@ -66,6 +66,24 @@ struct StepSmem {
 
 // LJ energy (already *4), force and in-cutoff count of molecule i at (px,py,pz) against the staged
 // configuration; `self` is i's own index in that configuration (skipped)
+// pair_exact without the early exit: the 12-6 terms are formed unconditionally and zeroed by selects when the pair is
+// outside the true cutoff (adding 0.0 changes no sum), so two of them can be in flight at once - the hit loops below
+// take two partners per iteration; their dependent FP64 chains (~250 cycles each) are what bounds the condensed phase.
+__device__ __forceinline__ bool pair_terms_nb(const Box &b, double px, double py, double pz, double jx, double jy, double jz,
+                                              double &e, double &gx, double &gy, double &gz)
+{
+    double dx, dy, dz;
+    const double r2 = pair_sep<false>(b, px, py, pz, jx, jy, jz, dx, dy, dz);
+    const bool in = r2 < b.rc2;
+    const double i2 = fast_rcp(in ? r2 : 1.0);
+    const double i6 = i2 * i2 * i2;
+    const double et = fma(i6, i6, -i6);
+    const double g = i2 * i6 * fma(48.0, i6, -24.0);
+    e = in ? et : 0.0;
+    gx = in ? g * dx : 0.0; gy = in ? g * dy : 0.0; gz = in ? g * dz : 0.0;
+    return in;
+}
+
 // Every lane of the warp must call the pair-loop helpers below together (`act` = this lane has a molecule): after
 // each divergent hit loop the warp is re-converged with __syncwarp(), otherwise the lanes that leave a hit loop
 // early run ahead into the next chunk's screen on their own and the screens execute with a fraction of the warp
@@ -213,17 +231,23 @@ __device__ __forceinline__ void half_shell_exact(const Box &b, const StepSmem &s
         const unsigned *words = (dir == 0 ? s.fw : s.bw) + i * s.NW;
         for (int c = 0; c < s.NW; c++) {
             unsigned w = act ? words[c] : 0u;
-            while (w) {
-                const int d = 32 * c + __ffs(w);
+            while (w) {                                   // two partners per iteration, ascending offsets
+                const int d1 = 32 * c + __ffs(w);
                 w &= w - 1;
-                int j = dir == 0 ? i + d : i - d;
-                if (j >= N) j -= N;
-                if (j < 0) j += N;
-                double et, gx, gy, gz;
-                if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
-                    e += et; fx += gx; fy += gy; fz += gz;
-                    cnt++;
-                }
+                const bool two = w != 0u;
+                const int d2 = two ? 32 * c + __ffs(w) : d1;
+                w &= w - 1;                               // (0 stays 0)
+                int j1 = dir == 0 ? i + d1 : i - d1, j2 = dir == 0 ? i + d2 : i - d2;
+                if (j1 >= N) j1 -= N;
+                if (j1 < 0) j1 += N;
+                if (j2 >= N) j2 -= N;
+                if (j2 < 0) j2 += N;
+                double e1, x1, y1, z1, e2, x2, y2, z2;
+                const bool in1 = pair_terms_nb(b, px, py, pz, s.x[j1], s.y[j1], s.z[j1], e1, x1, y1, z1);
+                const bool in2 = pair_terms_nb(b, px, py, pz, s.x[j2], s.y[j2], s.z[j2], e2, x2, y2, z2) && two;
+                e += e1; fx += x1; fy += y1; fz += z1;
+                if (in2) { e += e2; fx += x2; fy += y2; fz += z2; }
+                cnt += (in1 ? 1u : 0u) + (in2 ? 1u : 0u);
             }
             __syncwarp();
         }
