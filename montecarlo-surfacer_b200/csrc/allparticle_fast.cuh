@@ -66,24 +66,6 @@ struct StepSmem {
 
 // LJ energy (already *4), force and in-cutoff count of molecule i at (px,py,pz) against the staged
 // configuration; `self` is i's own index in that configuration (skipped)
-// pair_exact without the early exit: the 12-6 terms are formed unconditionally and zeroed by selects when the pair is
-// outside the true cutoff (adding 0.0 changes no sum), so two of them can be in flight at once - the hit loops below
-// take two partners per iteration; their dependent FP64 chains (~250 cycles each) are what bounds the condensed phase.
-__device__ __forceinline__ bool pair_terms_nb(const Box &b, double px, double py, double pz, double jx, double jy, double jz,
-                                              double &e, double &gx, double &gy, double &gz)
-{
-    double dx, dy, dz;
-    const double r2 = pair_sep<false>(b, px, py, pz, jx, jy, jz, dx, dy, dz);
-    const bool in = r2 < b.rc2;
-    const double i2 = fast_rcp(in ? r2 : 1.0);
-    const double i6 = i2 * i2 * i2;
-    const double et = fma(i6, i6, -i6);
-    const double g = i2 * i6 * fma(48.0, i6, -24.0);
-    e = in ? et : 0.0;
-    gx = in ? g * dx : 0.0; gy = in ? g * dy : 0.0; gz = in ? g * dz : 0.0;
-    return in;
-}
-
 // Every lane of the warp must call the pair-loop helpers below together (`act` = this lane has a molecule): after
 // each divergent hit loop the warp is re-converged with __syncwarp(), otherwise the lanes that leave a hit loop
 // early run ahead into the next chunk's screen on their own and the screens execute with a fraction of the warp

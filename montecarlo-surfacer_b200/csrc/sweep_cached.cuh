@@ -167,6 +167,25 @@ __device__ __forceinline__ bool pair_exact(const Box &b, double px, double py, d
     return true;
 }
 
+// pair_exact without the early exit: the 12-6 terms are formed unconditionally and zeroed by selects when the pair is
+// outside the true cutoff (adding 0.0 changes no sum), so two of them can be in flight at once - the hit loops below
+// of allparticle_fast.cuh take two partners per iteration; their dependent FP64 chains (~250 cycles each) bound the
+// condensed phase.  (In the sweep kernel, where a lane usually holds ONE partner, the second evaluation only costs: tried, slower.)
+__device__ __forceinline__ bool pair_terms_nb(const Box &b, double px, double py, double pz, double jx, double jy, double jz,
+                                              double &e, double &gx, double &gy, double &gz)
+{
+    double dx, dy, dz;
+    const double r2 = pair_sep<false>(b, px, py, pz, jx, jy, jz, dx, dy, dz);
+    const bool in = r2 < b.rc2;
+    const double i2 = fast_rcp(in ? r2 : 1.0);
+    const double i6 = i2 * i2 * i2;
+    const double et = fma(i6, i6, -i6);
+    const double g = i2 * i6 * fma(48.0, i6, -24.0);
+    e = in ? et : 0.0;
+    gx = in ? g * dx : 0.0; gy = in ? g * dy : 0.0; gz = in ? g * dz : 0.0;
+    return in;
+}
+
 // phase 2 for the point p: add the terms of the lane's hits; returns the mask of slots
 // that are truly inside the cutoff
 __device__ __forceinline__ unsigned add_hits(const Box &b, const ChainSmem &s, int lane, unsigned hits,
