@@ -58,6 +58,8 @@ def parse():
                          "16 T x 4 Lz x 4 wall-strength grid x 256 replicas, sharded over the GPUs, one observable group per "
                          "grid point (configs[3]); largeN: 256 chains x N=4096 in total, sharded over the GPUs (configs[4], "
                          "all-particle kernel with thread-block clusters)")
+    ap.add_argument("--largeN-sweep", action="store_true",
+                    help="largeN workload with the reference's sweep (block-per-chain kernel, N > 512) instead of the all-particle step")
     ap.add_argument("--start", default="lattice", choices=["lattice", "droplet"],
                     help="lattice: initializeBox's dilute fcc lattice (the reference's start); droplet: all molecules condensed "
                          "on the lower wall (jittered simple-cubic block, spacing 1.12: ~80 partners inside the cutoff each) - "
@@ -239,7 +241,7 @@ def main():
     Cn, N, S = args.chains or 8192, N_PART, args.sweeps_per_step
     total_largeN = 256
     if args.workload == "largeN":                   # configs[4]: 256 chains x N=4096 in total, strong-sharded
-        N, args.kernel = 4096, "allparticle"
+        N, args.kernel = 4096, ("sweep" if args.largeN_sweep else "allparticle")
         Cn = args.chains or smcb.shard_chains(256, world, rank).nchains      # --chains 32 emulates one rank of 8
         total_largeN = float(world) * Cn if args.chains else 256.0
     grid = None

@@ -113,7 +113,8 @@ int smcb_evaluate(smcb_engine *e, int mode,
 
 /* ---- the sweep (row a1: oneParticleMoves, SMC.c:278-351) -----------------
  * nsweeps sweeps of N sequential single-particle Smart-MC trials per chain
- * (N <= 512: one warp per chain; larger N: use the all-particle step).
+ * (N <= 512: one warp per chain, SMCB_FAST or SMCB_STRICT; 512 < N <= 6016: one
+ * block per chain, SMCB_FAST only; beyond that use the all-particle step).
  * Running energy (+= Un-Um on acceptance, SMC.c:341) and acceptance counts
  * accumulate in the chain state (smcb_get_chain_state).
  *

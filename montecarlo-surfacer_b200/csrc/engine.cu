@@ -462,7 +462,10 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
     if (rc) return rc;
     if (nsweeps < 0) return fail(SMCB_ERR_ARG, "nsweeps < 0");
     if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
-    if (e->N > kSweepMaxN) return fail(SMCB_ERR_ARG, "sweep kernel supports N <= %d (N = %d): use smcb_step_allparticle", kSweepMaxN, e->N);
+    if (e->N > kSweepMaxN && mode == SMCB_STRICT)
+        return fail(SMCB_ERR_ARG, "the STRICT (bit-exact) sweep kernel supports N <= %d (N = %d): use SMCB_FAST", kSweepMaxN, e->N);
+    if (e->N > kSweepBlockMaxN)
+        return fail(SMCB_ERR_ARG, "sweep kernels support N <= %d (N = %d): use smcb_step_allparticle", kSweepBlockMaxN, e->N);
     if (nsweeps == 0) return SMCB_OK;
     if (!e->energy_valid && (rc = refresh_energy(e, mode))) return rc;
     SweepArgs a{};

@@ -23,5 +23,7 @@ cudaError_t launch_dfma_peak(double *out, int blocks, int threads, int iters, cu
 
 // largest N the warp-per-chain sweep kernel is instantiated for
 constexpr int kSweepMaxN = 512;
+// largest N of the block-per-chain FAST sweep (positions twice in shared memory next to 10 KB of scratch)
+constexpr int kSweepBlockMaxN = 6016;
 
 }  // namespace smcb

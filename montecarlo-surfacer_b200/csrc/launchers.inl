@@ -75,8 +75,30 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
     return cudaGetLastError();
 }
 
+#if !SMCB_TU_IS_STRICT
+// N > 512: one block per chain (sweep_block.cuh)
+static cudaError_t sweep_block_launch(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
+{
+    const int threads = 256;
+    const size_t smem = BlockSweepSmem::bytes(d.Npad, threads);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t err;
+    if (fed) {
+        if ((err = cudaFuncSetAttribute(k_sweep_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        k_sweep_block<true><<<d.C, threads, smem, st>>>(d, a);
+    } else {
+        if ((err = cudaFuncSetAttribute(k_sweep_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        k_sweep_block<false><<<d.C, threads, smem, st>>>(d, a);
+    }
+    return cudaGetLastError();
+}
+#endif
+
 cudaError_t SMCB_CAT(launch_sweep_, SMCB_TU_SUFFIX)(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
 {
+#if !SMCB_TU_IS_STRICT
+    if (d.N > kSweepMaxN) return sweep_block_launch(fed, d, a, st);
+#endif
     const int k = d.Npad / 32;
     if (k <= 1) return sweep_k<1>(fed, d, a, st);
     if (k <= 2) return sweep_k<2>(fed, d, a, st);

@@ -229,3 +229,46 @@ def test_fast_sweep_multi_sweep_launch_tracks_oracle(orc):
         np.testing.assert_array_equal(acc[:, c], flags)
         assert rel_err(R[c], Ro) < 1e-9
         assert abs(E[c] - Eo) <= 1e-9 * max(1.0, abs(Eo))
+
+
+@pytest.mark.parametrize("N,A", [(1024, 0.05), (600, 0.3)])
+def test_fast_sweep_large_N_block_kernel(orc, N, A):
+    """N > 512: the block-per-chain FAST sweep (csrc/sweep_block.cuh), teacher-forced against the oracle's
+    oneParticleMoves on the same fed random numbers: same accept decisions, positions and energy change within
+    1e-12; then several Philox sweeps in one launch with the running energy checked against a fresh evaluation"""
+    M, T = 3, 1.1
+    L, Lz = 33.0, 240.0
+    s = make_sys(N, M, L, Lz)
+    W = GOLDEN_W_M3.copy()
+    nchains, nsweeps = 3, 3
+    rng = np.random.default_rng(7 + N)
+    R = mixed_configs(N, L, Lz, nchains, seed=3 * N, orc=orc)
+    with smcb.Engine(nchains, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
+        for k in range(nsweeps):
+            streams = np.stack([make_stream(N, 1, rng) for _ in range(nchains)], axis=1)
+            displ, off, u = expand_streams(orc, N, A, streams)
+            eng.set_positions(R)
+            eng.refresh_energy(smcb.FAST)
+            E0 = eng.chain_state()[0]
+            acc = eng.sweep_fed(displ, off, u, mode=smcb.FAST, want_accepted=True)
+            Rg = eng.get_positions()
+            Eg = eng.chain_state()[0]
+            for c in range(nchains):
+                Eo0 = orc.energy(s, R[c]) + orc.walls_energy(s, R[c], W)
+                j, Eo, fl = orc.sweep(s, R[c], W, A, T, displ[0, c], off[0, c], u[0, c], Eo0, want_flags=True)
+                np.testing.assert_array_equal(acc[0, c], fl)
+                assert rel_err(Rg[c], R[c], floor=1.0) < 1e-12, (k, c)
+                assert abs((Eg[c] - E0[c]) - (Eo - Eo0)) <= 1e-11 * max(1.0, abs(Eo - Eo0), abs(Eo0))
+        assert acc.sum() > 0
+        eng.set_positions(R)
+        eng.set_rng(3, 0, 0)
+        Et, at = eng.sweep_traced(4, smcb.FAST)
+        E, na, nt = eng.chain_state()
+        ev = eng.evaluate(smcb.FAST, per_particle=False)
+        Erec = ev["U_lj"] + ev["U_wall"]
+        assert np.all(np.abs(E - Erec) <= 1e-9 * np.maximum(1.0, np.abs(Erec)))
+        np.testing.assert_array_equal(Et[-1], E)
+        assert at.sum() > 0 and np.all(at <= N)
+        with pytest.raises(smcb.SmcbError):                 # bit-exact mode is the warp kernel, N <= 512
+            eng.sweep(1, smcb.STRICT)
