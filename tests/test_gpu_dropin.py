@@ -181,3 +181,19 @@ def test_batched_c_driver_runs(tmp_path):
     assert mass == expected == samples * 108
     acc = float(out["mean_E"].split()[4])
     assert 0.8 < acc <= 1.0
+
+
+def test_reference_main_unchanged_N4096(tmp_path):
+    """the reference's main.c built with -DN=4096 against the drop-in: the reference itself cannot run this size
+    (its initializeBox leaves 96 molecules coincident); here the lattice tiles and sMC sweeps on
+    the block-per-chain kernel"""
+    exe = os.path.join(BUILD, "main_N4096")
+    if not os.path.exists(exe):
+        pytest.skip("main_N4096 not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "2", "6", "3", "1.1"], cwd=tmp_path, env=dict(os.environ, SMCB_SEED="11"),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Final results" in r.stdout and "nan" not in r.stdout.lower().split("final results")[1][:400]
+    out = next((tmp_path / "Data").iterdir())
+    last = next(out.glob("last_state_N4096_*.csv")).read_text().strip(",\n").split(",")
+    assert len(last) == 3 * 4096 and all(np.isfinite(float(x)) for x in last)
