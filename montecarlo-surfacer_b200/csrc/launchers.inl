@@ -79,7 +79,8 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
 // N > 512: one block per chain (sweep_block.cuh)
 static cudaError_t sweep_block_launch(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
 {
-    const int threads = 256;
+    int threads = 256;
+    if (const char *env = getenv("SMCB_BLOCK_SWEEP_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 512 && v % 32 == 0) threads = v; }
     const size_t smem = BlockSweepSmem::bytes(d.Npad, threads);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t err;

@@ -31,11 +31,25 @@ struct BlockSweepSmem {
     }
 };
 
+// block-wide sum of four values with ONE barrier: warp totals by the transposed butterfly, one slot per warp in
+// `buf` (4 * nwarps doubles), then every thread adds the slots in warp order (fixed order, identical everywhere).
+// The caller alternates between two buffers so that a buffer is never rewritten before everyone has read it.
+__device__ __forceinline__ void block_sum4_once(double (&v)[4], double *buf)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    warp_sum4(lane, v[0], v[1], v[2], v[3]);
+    if (lane == 0) { buf[4 * warp] = v[0]; buf[4 * warp + 1] = v[1]; buf[4 * warp + 2] = v[2]; buf[4 * warp + 3] = v[3]; }
+    __syncthreads();
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int w = 0; w < nwarps; w++) { t0 += buf[4 * w]; t1 += buf[4 * w + 1]; t2 += buf[4 * w + 2]; t3 += buf[4 * w + 3]; }
+    v[0] = t0; v[1] = t1; v[2] = t2; v[3] = t3;
+}
+
 // energy (already *4) and force of a particle at p against all others (index `self` skipped) and the surface;
 // every thread returns the block totals.  nin: this thread's partners inside the cutoff (for the pair counter).
 template <bool PZ>
 __device__ __forceinline__ void block_eval_point(const Box &b, const ScreenConsts &sc, const BlockSweepSmem &s, const double *__restrict__ W,
-                                                 int N, int Npad, int self, double px, double py, double pz,
+                                                 int N, int Npad, int self, double px, double py, double pz, int which,
                                                  double &U, double &Fx, double &Fy, double &Fz, unsigned &nin)
 {
     const int tid = threadIdx.x, T_ = blockDim.x;
@@ -45,7 +59,12 @@ __device__ __forceinline__ void block_eval_point(const Box &b, const ScreenConst
     const float2 *X2 = reinterpret_cast<const float2 *>(s.fx), *Y2 = reinterpret_cast<const float2 *>(s.fy),
                  *Z2 = reinterpret_cast<const float2 *>(s.fz);
     double v[4] = {0.0, 0.0, 0.0, 0.0};               // e, fx, fy, fz
-    for (int j2 = tid; j2 < Npad / 2; j2 += T_) {
+    // phase 1: screen this thread's partners (pairs j2 = tid, tid + T, ...), two bits per iteration; at most 16
+    // iterations (N <= 6016 with 256 threads).  Phase 2 evaluates the hits: kept out of the screen loop so that a
+    // warp runs max-over-lanes exact evaluations, not one per iteration in which any lane has a hit.
+    unsigned hits = 0;
+    int it = 0;
+    for (int j2 = tid; j2 < Npad / 2; j2 += T_, it++) {
         float2 sx = sub2(ax, X2[j2]);
         sx = sub2(sx, sub2(add2(sx, MG), MG));
         float2 sy = sub2(ay, Y2[j2]);
@@ -56,18 +75,20 @@ __device__ __forceinline__ void block_eval_point(const Box &b, const ScreenConst
             sz = fma2(sub2(add2(t, MG), MG), make_float2(-sc.zper, -sc.zper), sz);
         }
         const float2 r2 = fma2(sz, sz, fma2(sy, sy, mul2(sx, sx)));
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int j = 2 * j2 + h;
-            if ((h == 0 ? r2.x : r2.y) < sc.rc2s && j != self && j < N) {
-                double et, gx, gy, gz;
-                if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
-                    v[0] += et; v[1] += gx; v[2] += gy; v[3] += gz;
-                    nin++;
-                }
-            }
+        if (r2.x < sc.rc2s) hits |= 1u << (2 * it);
+        if (r2.y < sc.rc2s) hits |= 2u << (2 * it);
+    }
+    while (hits) {                                     // ascending j within the thread
+        const int bit = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int j = 2 * (tid + T_ * (bit >> 1)) + (bit & 1);
+        double et, gx, gy, gz;
+        if (j != self && j < N && pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
+            v[0] += et; v[1] += gx; v[2] += gy; v[3] += gz;
+            nin++;
         }
     }
+    __syncwarp();
     double ew = 0.0, fzw = 0.0;
     if (b.wall) {
         const double dzw = wall_dz<false>(b, pz);
@@ -91,7 +112,7 @@ __device__ __forceinline__ void block_eval_point(const Box &b, const ScreenConst
             }
         }
     }
-    block_sum<4>(v, s.scratch);
+    block_sum4_once(v, s.scratch + 64 * which);       // 4 * 16 warps per buffer; old / proposed position alternate
     U = 4.0 * (v[0] + ew); Fx = v[1]; Fy = v[2]; Fz = v[3] + fzw;
 }
 
@@ -156,12 +177,12 @@ __device__ __forceinline__ void sweep_block_body(const DevChains &d, const Sweep
                 if (n >= N) n -= N;
                 const double px = s.x[n], py = s.y[n], pz = s.z[n];
                 double Um, Fmx, Fmy, Fmz, Un, Fnx, Fny, Fnz;
-                block_eval_point<PZ>(b, sc, s, W, N, Npad, n, px, py, pz, Um, Fmx, Fmy, Fmz, cnt);          // SMC.c:300-304
+                block_eval_point<PZ>(b, sc, s, W, N, Npad, n, px, py, pz, 0, Um, Fmx, Fmy, Fmz, cnt);          // SMC.c:300-304
                 const double dX = fma(Fmx, AoT, s.g0[t]), dY = fma(Fmy, AoT, s.g1[t]), dZ = fma(Fmz, AoT, s.g2[t]);   // SMC.c:307-309
                 const double qx = min_image<false>(px + dX, b.L, b.invL), qy = min_image<false>(py + dY, b.L, b.invL);   // SMC.c:311-316
                 double qz = pz + dZ;
                 if (PZ) qz = min_image<false>(qz, b.Lz, b.invLz);
-                block_eval_point<PZ>(b, sc, s, W, N, Npad, n, qx, qy, qz, Un, Fnx, Fny, Fnz, cnt);          // SMC.c:319-321
+                block_eval_point<PZ>(b, sc, s, W, N, Npad, n, qx, qy, qz, 1, Un, Fnx, Fny, Fnz, cnt);          // SMC.c:319-321
                 // SMC.c:326-335: accept iff u < exp(-(Un-Um + d.(Fn+Fm)/2 + (Fn^2-Fm^2) A/(4T))/T)
                 const double f2 = fma(Fnx, Fnx, fma(Fny, Fny, Fnz * Fnz)) - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
                 const double dr = fma(dX, Fnx + Fmx, fma(dY, Fny + Fmy, dZ * (Fnz + Fmz)));
@@ -197,7 +218,7 @@ __device__ __forceinline__ void sweep_block_body(const DevChains &d, const Sweep
 }
 
 template <bool FED>
-__global__ void __launch_bounds__(256) k_sweep_block(DevChains d, SweepArgs a)
+__global__ void __launch_bounds__(512) k_sweep_block(DevChains d, SweepArgs a)
 {
     if (chain_params(d, blockIdx.x).flags & SMCB_PERIODIC_Z) sweep_block_body<FED, true>(d, a);
     else sweep_block_body<FED, false>(d, a);
