@@ -272,3 +272,44 @@ def test_fast_sweep_large_N_block_kernel(orc, N, A):
         assert at.sum() > 0 and np.all(at <= N)
         with pytest.raises(smcb.SmcbError):                 # bit-exact mode is the warp kernel, N <= 512
             eng.sweep(1, smcb.STRICT)
+
+
+def test_block_sweep_N4096_and_bulk_mode(orc):
+    """the block-per-chain sweep at the BASELINE configs[4] size (N = 4096, corrected 16x16x4 fcc lattice) and in
+    bulk mode (z periodic): running energy equals a fresh evaluation, x,y stay in the box, acceptance is sane"""
+    N, M = 4096, 3
+    L, Lz = 33.0, 240.0
+    X = orc.fcc_lattice(L, Lz, 16, 16, 4)
+    rng = np.random.default_rng(1)
+    R0 = np.stack([X + 0.02 * rng.standard_normal(3 * N) for _ in range(3)])
+    with smcb.Engine(3, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=1.1, A=0.01), GOLDEN_W_M3)
+        eng.set_positions(R0)
+        eng.set_rng(8, 0, 0)
+        eng.sweep(2, smcb.FAST)
+        E, na, nt = eng.chain_state()
+        ev = eng.evaluate(smcb.FAST, per_particle=False)
+        R = eng.get_positions().reshape(3, N, 3)
+    Erec = ev["U_lj"] + ev["U_wall"]
+    assert np.all(np.abs(E - Erec) <= 1e-9 * np.maximum(1.0, np.abs(Erec)))
+    assert np.all(nt == 2 * N) and np.all(na > 0.2 * nt) and np.all(na < nt)
+    assert np.all(np.abs(R[:, :, :2]) <= L / 2 + 1e-12)
+    # bulk: N = 864 liquid-like fcc, rho* = 0.8, 3-D minimum image, cutoff 3
+    Nb = 864
+    Lb = (Nb / 0.8) ** (1 / 3)
+    cells = np.array([(i, j, k) for i in range(6) for j in range(6) for k in range(6)], dtype=float)
+    basis = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]])
+    Xb = ((cells[:, None, :] + basis[None]).reshape(-1, 3) * (Lb / 6) - Lb / 2 + 0.1).reshape(-1)
+    sb = make_sys(Nb, 3, Lb, Lb, periodic_z=1, wall=0)
+    with smcb.Engine(2, Nb, 3) as eng:
+        eng.set_params(smcb.default_params(L=Lb, Lz=Lb, T=1.0, A=0.005, flags=smcb.PERIODIC_Z))
+        eng.broadcast_positions(Xb)
+        eng.set_rng(9, 0, 0)
+        eng.sweep(3, smcb.FAST)
+        E, na, nt = eng.chain_state()
+        Rb = eng.get_positions()
+    for c in range(2):
+        Eo = orc.energy(sb, Rb[c])
+        assert abs(E[c] - Eo) <= 1e-9 * abs(Eo)
+        assert np.all(np.abs(Rb[c]) <= Lb / 2 + 1e-12)          # z wrapped too
+    assert na.sum() > 0
