@@ -63,8 +63,10 @@ __device__ __forceinline__ void block_eval_point(const Box &b, const ScreenConst
     // iterations (N <= 6016 with 256 threads).  Phase 2 evaluates the hits: kept out of the screen loop so that a
     // warp runs max-over-lanes exact evaluations, not one per iteration in which any lane has a hit.
     unsigned hits = 0;
-    int it = 0;
-    for (int j2 = tid; j2 < Npad / 2; j2 += T_, it++) {
+    const int nit = (Npad / 2 - tid + T_ - 1) / T_;   // this thread's iterations
+#pragma unroll 4
+    for (int it = 0; it < nit; it++) {
+        const int j2 = tid + it * T_;
         float2 sx = sub2(ax, X2[j2]);
         sx = sub2(sx, sub2(add2(sx, MG), MG));
         float2 sy = sub2(ay, Y2[j2]);
