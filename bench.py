@@ -463,7 +463,7 @@ def main():
                                  "cutoff screen runs in packed FP32 (exact FP64 for the pairs inside), so frac is a figure of "
                                  "merit against the FP64 peak, not FP64-pipe utilisation - that is in profiles/ (ncu).  peak = "
                                  "DFMA peak measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"},
-            "clocks": main["clocks"], "gpu_launches": args.steps * 3, "device": info,
+            "clocks": main["clocks"], "gpu_launches": args.steps * 4, "device": info,
         }
         line.update(extra)
         if e2e:

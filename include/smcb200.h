@@ -167,9 +167,8 @@ int smcb_reset_counters(smcb_engine *e);
  *   reference writes them, SMC.c:140).
  * The block is one contiguous array of uint64 counters followed by doubles per
  * group (layout from smcb_obs_layout); it is the ONLY thing ranks all-reduce.
- * Counters are exact (integer atomics).  The moments are accumulated over chains with
- * double-precision atomics, so their last bits depend on the order chains retire; chain
- * state (positions, energies, accept counts) is always bit-reproducible. */
+ * Counters are exact (integer atomics) and the moments are summed over the chains of a
+ * group in chain order, so the block - like the chain state - is bit-reproducible. */
 typedef struct smcb_obs_layout {
     int ngroups;
     int nvox;            /* 33*33*33                                   */

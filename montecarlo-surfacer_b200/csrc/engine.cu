@@ -67,7 +67,7 @@ struct smcb_engine {
     DevBuf<unsigned long long> pairs, counters;
     DevBuf<unsigned char> fed_acc;
     DevBuf<int> rbin, trace_acc;
-    DevBuf<double> eval_partials;
+    DevBuf<double> eval_partials, chain_mom;
     DevBuf<unsigned> eval_tickets;
     DevBuf<double> trace_E;
     uint64_t seed = 0x5eed5eedull, step = 0;
@@ -191,7 +191,7 @@ int smcb_destroy(smcb_engine *e)
     e->F.release(); e->Fn.release(); e->dl.release(); e->e_lj.release(); e->f_lj.release();
     e->e_wall.release(); e->f_wall.release(); e->totals.release(); e->moments.release();
     e->peak_out.release(); e->fed_a.release(); e->fed_b.release(); e->nacc.release(); e->ntri.release();
-    e->cache_out.release(); e->eval_partials.release(); e->eval_tickets.release(); e->trace_E.release(); e->trace_acc.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
+    e->cache_out.release(); e->chain_mom.release(); e->eval_partials.release(); e->eval_tickets.release(); e->trace_E.release(); e->trace_acc.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -619,14 +619,16 @@ int smcb_gather(smcb_engine *e)
     CK(cudaEventRecord(e->ev0, e->stream));
     if ((rc = run_evaluate(e, SMCB_FAST, o))) return rc;
     GatherArgs g{};
+    CK(e->chain_mom.ensure((size_t)e->C * 5));
     g.totals = e->totals.p; g.rbin = e->rbin.p; g.counters = e->counters.p; g.moments = e->moments.p;
+    g.chain_mom = e->chain_mom.p; g.ngroups = e->ngroups;
     g.u64_per_group = e->u64_per_group(); g.f64_per_group = e->f64_per_group();
     g.nebins = e->nebins; g.e_lo = e->e_lo; g.e_hi = e->e_hi;
     CK(launch_gather(e->chains(), g, e->stream));
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
-    e->last_launches = 2;
+    e->last_launches = 3;
     return SMCB_OK;
 }
 

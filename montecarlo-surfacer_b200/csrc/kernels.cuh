@@ -579,6 +579,8 @@ struct GatherArgs {
     int *rbin;                     // [C][N]
     unsigned long long *counters;  // [G][u64_per_group]
     double *moments;               // [G][f64_per_group]
+    double *chain_mom;             // [C][5] this gather's contribution of every chain (summed per group in fixed order)
+    int ngroups;
     size_t u64_per_group, f64_per_group;
     int nebins;
     double e_lo, e_hi;
@@ -589,7 +591,9 @@ struct GatherArgs {
 // localDensityAndMobility (SMC.c:912-927) for every chain into its group's
 // voxel block, plus the z profile, the energy histogram and the moments sMC
 // accumulates at a gather (SMC.c:137-141).  Counters are exact (integer
-// atomics); moments use double atomics.
+// atomics, order-independent); the floating-point moments are written per chain and
+// summed per group in a fixed order by k_gather_moments, so the whole observable
+// block is bit-reproducible.
 __global__ void k_gather(DevChains d, GatherArgs g)
 {
     const int chain = blockIdx.x, N = d.N, Npad = d.Npad;
@@ -617,18 +621,36 @@ __global__ void k_gather(DevChains d, GatherArgs g)
         const double E = t[0] + t[1];
         const double vol3 = 3 * cp.L * cp.L * cp.Lz;
         const double Pv = -t[2] / vol3 + (-t[3] / vol3);    // pressure() + wallsPressure()  SMC.c:140
-        double *m = g.moments + (size_t)cp.group * g.f64_per_group;
-        atomicAdd(m + 0, E);
-        atomicAdd(m + 1, E * E);
-        atomicAdd(m + 2, Pv);
-        atomicAdd(m + 3, Pv * Pv);
+        double *m = g.chain_mom + (size_t)chain * 5;
         const long long tri = d.ntri[chain];
-        atomicAdd(m + 4, tri > 0 ? (double)d.nacc[chain] / (double)tri : 0.0);
+        m[0] = E; m[1] = E * E; m[2] = Pv; m[3] = Pv * Pv;
+        m[4] = tri > 0 ? (double)d.nacc[chain] / (double)tri : 0.0;
         const double epp = E / N;
         int bin = (int)floor((epp - g.e_lo) / (g.e_hi - g.e_lo) * g.nebins);
         bin = bin < 0 ? 0 : (bin >= g.nebins ? g.nebins - 1 : bin);
         atomicAdd(ehist + bin, 1ull);
         atomicAdd(nsamp, 1ull);
+    }
+}
+
+// One block per observable group: the chains of the group are visited in chain order (thread t takes chains
+// t, t + blockDim, ...; then a fixed-order block sum), and the single writer adds the totals to the group's moments.
+__global__ void k_gather_moments(DevChains d, GatherArgs g)
+{
+    const int grp = blockIdx.x;
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+        if ((int)chain_params(d, c).group != grp) continue;
+        const double *m = g.chain_mom + (size_t)c * 5;
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[k] += m[k];
+    }
+    __shared__ double scratch[8 * 32];
+    block_sum<5>(v, scratch);
+    if (threadIdx.x == 0) {
+        double *m = g.moments + (size_t)grp * g.f64_per_group;
+#pragma unroll
+        for (int k = 0; k < 5; k++) m[k] += v[k];
     }
 }
 

@@ -13,6 +13,7 @@ namespace smcb {
 cudaError_t launch_gather(const DevChains &d, const GatherArgs &g, cudaStream_t st)
 {
     k_gather<<<d.C, 128, 0, st>>>(d, g);
+    k_gather_moments<<<g.ngroups, 256, 0, st>>>(d, g);
     return cudaGetLastError();
 }
 
