@@ -603,6 +603,9 @@ __global__ void k_gather(DevChains d, GatherArgs g)
     const int nvox = SMCB_NCX * SMCB_NCX * SMCB_NCZ;
     unsigned long long *D = cnt, *Mu = cnt + nvox, *zprof = cnt + 2 * nvox, *ehist = zprof + SMCB_NCZ,
                        *nsamp = ehist + g.nebins;
+    __shared__ unsigned zloc[SMCB_NCZ];            // the chain's z profile first: 33 hot addresses would serialise in L2
+    for (int k = threadIdx.x; k < SMCB_NCZ; k += blockDim.x) zloc[k] = 0u;
+    __syncthreads();
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         // uint8_t i = floor((x/L+.5)*Ncx) ...  (SMC.c:917-919; the uint8_t wrap is kept)
         const int i = (int)floor((P[n] / cp.L + .5) * SMCB_NCX) & 0xff;
@@ -614,8 +617,11 @@ __global__ void k_gather(DevChains d, GatherArgs g)
             int *rb = g.rbin + (size_t)chain * N + n;
             if (*rb != v) { atomicAdd(Mu + v, 1ull); *rb = v; }
         }
-        if (k < SMCB_NCZ) atomicAdd(zprof + k, 1ull);
+        if (k < SMCB_NCZ) atomicAdd(zloc + k, 1u);
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SMCB_NCZ; k += blockDim.x)
+        if (zloc[k]) atomicAdd(zprof + k, (unsigned long long)zloc[k]);
     if (threadIdx.x == 0) {
         const double *t = g.totals + (size_t)chain * 4;
         const double E = t[0] + t[1];
