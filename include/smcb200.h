@@ -111,6 +111,15 @@ int smcb_evaluate(smcb_engine *e, int mode,
                   double *e_lj, double *f_lj, double *e_wall, double *f_wall,
                   double *U_lj, double *U_wall, double *vir_lj, double *vir_wall_ref);
 
+/* The wall virial as the reference MEANT it (its wallsPressure uses rz + L/2 instead of rz + Lz/2, has no
+ * clamp and adds the flat-wall term once per in-cutoff site, SMC.c:880,888-889 - SURVEY.md App. B3): distance
+ * to the nearer wall as in wallsEnergySingle, flat-wall term once, every site inside the cutoff.  Chain sums
+ * computed by the last smcb_evaluate / smcb_gather; the corrected wall pressure is -vir_wall/(3 L^2 Lz). */
+int smcb_get_wall_virial(smcb_engine *e, double *vir_wall);
+/* which one enters the pressure moments of smcb_gather: 0 = the reference's arithmetic (default, what sMC
+ * records, SMC.c:140), 1 = the corrected one */
+int smcb_obs_set_wall_virial(smcb_engine *e, int intended);
+
 /* ---- the sweep (row a1: oneParticleMoves, SMC.c:278-351) -----------------
  * nsweeps sweeps of N sequential single-particle Smart-MC trials per chain
  * (N <= 512: one warp per chain, SMCB_FAST or SMCB_STRICT; 512 < N <= 6016: one

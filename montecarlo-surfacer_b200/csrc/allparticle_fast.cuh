@@ -434,7 +434,7 @@ __device__ __forceinline__ void tile_load_wait(uint64_t *bar)
 // block of a chain to finish (atomic ticket) adds them in part order, so the totals do not depend on scheduling.
 struct EvalFastArgs {
     int parts;
-    double *partials;          // [C][parts][4]
+    double *partials;          // [C][parts][kTot]
     unsigned *tickets;         // [C], zeroed by the launcher's caller, left zero again by the kernel
 };
 
@@ -462,7 +462,7 @@ __device__ __forceinline__ void evaluate_fast_body(const DevChains &d, const Eva
         s.fz[j] = j < N ? (float)(s.z[j] * b.invL) : 3.0e18f;
     }
     __syncthreads();
-    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    double tot[kTot] = {0.0, 0.0, 0.0, 0.0, 0.0};
     unsigned cnt = 0;
     for (int i0 = 0; i0 < N; i0 += parts * T_) {            // uniform trip count: the pair loop re-converges the warp
         const int i = i0 + part + parts * tid;
@@ -476,6 +476,7 @@ __device__ __forceinline__ void evaluate_fast_body(const DevChains &d, const Eva
         if (b.wall) {
             e_wall = wall_point_fast(b, W, px, py, pz, wx, wy, wz) * 4;
             tot[3] += wall_virial_ref<false>(b, W, px, py, pz);
+            tot[4] += wall_virial_intended<false>(b, W, px, py, pz);
         }
         const size_t q = (size_t)chain * Npad + i, q3 = (size_t)chain * 3 * Npad + i;
         if (o.e_lj) o.e_lj[q] = e_lj;
@@ -486,23 +487,23 @@ __device__ __forceinline__ void evaluate_fast_body(const DevChains &d, const Eva
         tot[1] += e_wall;
         tot[2] += 0.5 * vir;
     }
-    block_sum<4>(tot, s.scratch);
+    block_sum<kTot>(tot, s.scratch);
     if (!o.totals) return;
-    double *mine = ea.partials + ((size_t)chain * parts + part) * 4;
+    double *mine = ea.partials + ((size_t)chain * parts + part) * kTot;
     if (tid == 0) {
-        mine[0] = tot[0]; mine[1] = tot[1]; mine[2] = tot[2]; mine[3] = tot[3];
+        for (int k = 0; k < kTot; k++) mine[k] = tot[k];
         __threadfence();
         s_last = atomicAdd(ea.tickets + chain, 1u) == (unsigned)(parts - 1);
     }
     __syncthreads();
     if (s_last && tid == 0) {
         __threadfence();
-        const double *pp = ea.partials + (size_t)chain * parts * 4;
-        double r[4] = {0.0, 0.0, 0.0, 0.0};
+        const double *pp = ea.partials + (size_t)chain * parts * kTot;
+        double r[kTot] = {0.0, 0.0, 0.0, 0.0, 0.0};
         for (int p = 0; p < parts; p++)
-            for (int k = 0; k < 4; k++) r[k] += pp[4 * p + k];
-        double *t = o.totals + (size_t)chain * 4;
-        t[0] = r[0]; t[1] = r[1]; t[2] = r[2]; t[3] = r[3];
+            for (int k = 0; k < kTot; k++) r[k] += pp[kTot * p + k];
+        double *t = o.totals + (size_t)chain * kTot;
+        for (int k = 0; k < kTot; k++) t[k] = r[k];
         ea.tickets[chain] = 0;
     }
 }

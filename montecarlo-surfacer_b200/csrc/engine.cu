@@ -63,6 +63,8 @@ struct smcb_engine {
     DevBuf<double> fed_a, fed_b;            // host-fed random inputs
     DevBuf<double> cache_out;               // test hook (smcb_debug_capture_cache)
     bool capture_cache = false;
+    bool wall_virial_intended = false;      // which wall virial the gathered pressure uses (smcb_obs_set_wall_virial)
+    bool totals_valid = false;              // totals hold the last smcb_evaluate / smcb_gather
     DevBuf<long long> nacc, ntri, fed_off;
     DevBuf<unsigned long long> pairs, counters;
     DevBuf<unsigned char> fed_acc;
@@ -165,7 +167,7 @@ int smcb_create(smcb_engine **out, int device, int nchains, int N, int M)
     if (a == cudaSuccess) a = e->nacc.ensure(nchains);
     if (a == cudaSuccess) a = e->ntri.ensure(nchains);
     if (a == cudaSuccess) a = e->pairs.ensure(2);
-    if (a == cudaSuccess) a = e->totals.ensure((size_t)4 * nchains);
+    if (a == cudaSuccess) a = e->totals.ensure((size_t)kTot * nchains);
     if (a == cudaSuccess) a = e->rbin.ensure((size_t)nchains * N);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->E.p, 0, nchains * sizeof(double), e->stream);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->nacc.p, 0, nchains * sizeof(long long), e->stream);
@@ -329,7 +331,7 @@ static int run_evaluate(smcb_engine *e, int mode, const EvalOut &o)
     }
     // FAST: packed-FP32 screened pair loop, several blocks per chain when the batch is small
     const int parts = evaluate_fast_parts(d);
-    CK(e->eval_partials.ensure((size_t)e->C * parts * 4));
+    CK(e->eval_partials.ensure((size_t)e->C * parts * kTot));
     if (e->eval_tickets.n < (size_t)e->C) {
         CK(e->eval_tickets.ensure(e->C));
         CK(cudaMemsetAsync(e->eval_tickets.p, 0, e->C * sizeof(unsigned), e->stream));
@@ -367,19 +369,20 @@ int smcb_evaluate(smcb_engine *e, int mode, double *e_lj, double *f_lj, double *
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
     e->last_launches = 1;
+    e->totals_valid = true;
     if (e_lj && (rc = fetch(e, o.e_lj, e_lj, 1))) return rc;
     if (f_lj && (rc = fetch(e, o.f_lj, f_lj, 3))) return rc;
     if (e_wall && (rc = fetch(e, o.e_wall, e_wall, 1))) return rc;
     if (f_wall && (rc = fetch(e, o.f_wall, f_wall, 3))) return rc;
     if (U_lj || U_wall || vir_lj || vir_wall_ref) {
-        std::vector<double> t((size_t)4 * e->C);
+        std::vector<double> t((size_t)kTot * e->C);
         CK(cudaMemcpyAsync(t.data(), e->totals.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         for (int c = 0; c < e->C; c++) {
-            if (U_lj) U_lj[c] = t[4 * c];
-            if (U_wall) U_wall[c] = t[4 * c + 1];
-            if (vir_lj) vir_lj[c] = t[4 * c + 2];
-            if (vir_wall_ref) vir_wall_ref[c] = t[4 * c + 3];
+            if (U_lj) U_lj[c] = t[kTot * c];
+            if (U_wall) U_wall[c] = t[kTot * c + 1];
+            if (vir_lj) vir_lj[c] = t[kTot * c + 2];
+            if (vir_wall_ref) vir_wall_ref[c] = t[kTot * c + 3];
         }
     }
     return SMCB_OK;
@@ -392,12 +395,12 @@ static int refresh_energy(smcb_engine *e, int mode)
     o.totals = e->totals.p;
     int rc = run_evaluate(e, mode, o);
     if (rc) return rc;
-    // E[c] = totals[4c] + totals[4c+1]: strided 2-D copies then an add would need a kernel;
+    // E[c] = totals[c][0] + totals[c][1]: strided 2-D copies then an add would need a kernel;
     // C is small next to a sweep, do it through the host once.
-    std::vector<double> t((size_t)4 * e->C), E(e->C);
+    std::vector<double> t((size_t)kTot * e->C), E(e->C);
     CK(cudaMemcpyAsync(t.data(), e->totals.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    for (int c = 0; c < e->C; c++) E[c] = t[4 * c] + t[4 * c + 1];
+    for (int c = 0; c < e->C; c++) E[c] = t[kTot * c] + t[kTot * c + 1];
     CK(cudaMemcpyAsync(e->E.p, E.data(), E.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->energy_valid = true;
@@ -622,6 +625,7 @@ int smcb_gather(smcb_engine *e)
     CK(e->chain_mom.ensure((size_t)e->C * 5));
     g.totals = e->totals.p; g.rbin = e->rbin.p; g.counters = e->counters.p; g.moments = e->moments.p;
     g.chain_mom = e->chain_mom.p; g.ngroups = e->ngroups;
+    g.wall_virial_intended = e->wall_virial_intended ? 1 : 0;
     g.u64_per_group = e->u64_per_group(); g.f64_per_group = e->f64_per_group();
     g.nebins = e->nebins; g.e_lo = e->e_lo; g.e_hi = e->e_hi;
     CK(launch_gather(e->chains(), g, e->stream));
@@ -629,6 +633,7 @@ int smcb_gather(smcb_engine *e)
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
     e->last_launches = 3;
+    e->totals_valid = true;
     return SMCB_OK;
 }
 
@@ -761,6 +766,27 @@ int smcb_set_rbin(smcb_engine *e, const int32_t *rbin)
     if (!rbin) return fail(SMCB_ERR_ARG, "rbin is null");
     CK(cudaMemcpyAsync(e->rbin.p, rbin, (size_t)e->C * e->N * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    return SMCB_OK;
+}
+
+// ---- the wall virial as the reference meant it -------------------------------
+int smcb_get_wall_virial(smcb_engine *e, double *vir_wall)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!vir_wall) return fail(SMCB_ERR_ARG, "vir_wall is null");
+    if (!e->totals_valid) return fail(SMCB_ERR_STATE, "call smcb_evaluate or smcb_gather first");
+    std::vector<double> t((size_t)kTot * e->C);
+    CK(cudaMemcpyAsync(t.data(), e->totals.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < e->C; c++) vir_wall[c] = t[kTot * c + 4];
+    return SMCB_OK;
+}
+
+int smcb_obs_set_wall_virial(smcb_engine *e, int intended)
+{
+    if (!e) return fail(SMCB_ERR_ARG, "null engine");
+    e->wall_virial_intended = intended != 0;
     return SMCB_OK;
 }
 

@@ -33,9 +33,11 @@ struct DevChains {
     unsigned long long *pair_counts;   // [0] ordered pairs evaluated, [1] of them inside the cutoff
 };
 
+constexpr int kTot = 5;      // chain totals: U_lj, U_wall, vir_lj, vir_wall_ref (as the reference writes it), vir_wall (as it meant it)
+
 struct EvalOut {              // all nullable, SoA
     double *e_lj, *f_lj, *e_wall, *f_wall;   // [C][Npad], [C][3][Npad]
-    double *totals;                          // [C][4]: U_lj, U_wall, vir_lj, vir_wall_ref
+    double *totals;                          // [C][kTot]
 };
 
 struct RngArgs {
@@ -120,7 +122,7 @@ __global__ void k_evaluate(DevChains d, EvalOut o)
         sx[j] = P[j]; sy[j] = P[Npad + j]; sz[j] = P[2 * Npad + j];
     }
     __syncthreads();
-    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    double tot[kTot] = {0.0, 0.0, 0.0, 0.0, 0.0};
     unsigned long long cnt = 0;
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
         double e_lj, e_wall, fx, fy, fz, wx, wy, wz, vir;
@@ -133,12 +135,15 @@ __global__ void k_evaluate(DevChains d, EvalOut o)
         tot[0] += 0.5 * e_lj;
         tot[1] += e_wall;
         tot[2] += 0.5 * vir;
-        if (b.wall) tot[3] += wall_virial_ref<STRICT>(b, W, sx[i], sy[i], sz[i]);
+        if (b.wall) {
+            tot[3] += wall_virial_ref<STRICT>(b, W, sx[i], sy[i], sz[i]);
+            tot[4] += wall_virial_intended<STRICT>(b, W, sx[i], sy[i], sz[i]);
+        }
     }
-    block_sum<4>(tot, scratch);
+    block_sum<kTot>(tot, scratch);
     if (threadIdx.x == 0 && o.totals) {
-        double *t = o.totals + (size_t)chain * 4;
-        t[0] = tot[0]; t[1] = tot[1]; t[2] = tot[2]; t[3] = tot[3];
+        double *t = o.totals + (size_t)chain * kTot;
+        for (int k = 0; k < kTot; k++) t[k] = tot[k];
     }
 }
 
@@ -575,7 +580,8 @@ __global__ void k_allparticle(DevChains d, StepArgs a)
 
 // =============================================================== k_gather ===
 struct GatherArgs {
-    const double *totals;          // [C][4] from k_evaluate (FAST): U_lj, U_wall, vir_lj, vir_wall_ref
+    const double *totals;          // [C][kTot] from the FAST evaluation
+    int wall_virial_intended;      // 0: P uses the reference's wallsPressure arithmetic (default), 1: the intended wall virial
     int *rbin;                     // [C][N]
     unsigned long long *counters;  // [G][u64_per_group]
     double *moments;               // [G][f64_per_group]
@@ -623,10 +629,10 @@ __global__ void k_gather(DevChains d, GatherArgs g)
     for (int k = threadIdx.x; k < SMCB_NCZ; k += blockDim.x)
         if (zloc[k]) atomicAdd(zprof + k, (unsigned long long)zloc[k]);
     if (threadIdx.x == 0) {
-        const double *t = g.totals + (size_t)chain * 4;
+        const double *t = g.totals + (size_t)chain * kTot;
         const double E = t[0] + t[1];
         const double vol3 = 3 * cp.L * cp.L * cp.Lz;
-        const double Pv = -t[2] / vol3 + (-t[3] / vol3);    // pressure() + wallsPressure()  SMC.c:140
+        const double Pv = -t[2] / vol3 + (-t[g.wall_virial_intended ? 4 : 3] / vol3);    // pressure() + wallsPressure()  SMC.c:140
         double *m = g.chain_mom + (size_t)chain * 5;
         const long long tri = d.ntri[chain];
         m[0] = E; m[1] = E * E; m[2] = Pv; m[3] = Pv * Pv;

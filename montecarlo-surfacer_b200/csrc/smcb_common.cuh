@@ -200,6 +200,30 @@ __device__ __forceinline__ double wall_virial_ref(const Box &b, const double *__
     return acc;
 }
 
+// The wall virial the reference MEANT to compute: sum of r dV/dr over the surface terms of one
+// particle with the same geometry as wallsEnergySingle / wallsForce - distance to the nearer wall from rz + Lz/2
+// with the clamp (SMC.c:735-739), the flat-wall term ONCE, and every site inside the cutoff.
+template <bool STRICT>
+__device__ __forceinline__ double wall_virial_intended(const Box &b, const double *__restrict__ W, double rx, double ry, double rz)
+{
+    const double dw = b.L / b.M;
+    const double dz = wall_dz<STRICT>(b, rz);
+    const double z6 = dz * dz * dz * dz * dz * dz;
+    double acc = 24.0 * b.b0 / z6 - 48.0 * b.a0 / (z6 * z6);
+    for (int i = 0; i < b.M; i++)
+        for (int j = 0; j < b.M; j++) {
+            const int m = j + i * b.M;
+            const double dx = min_image<STRICT>(rx - i * dw, b.L, b.invL);
+            const double dy = min_image<STRICT>(ry - j * dw, b.L, b.invL);
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 < b.rc2) {
+                const double r6 = r2 * r2 * r2;
+                acc += 24.0 * W[2 * m + 1] / r6 - 48.0 * W[2 * m] / (r6 * r6);
+            }
+        }
+    return acc;
+}
+
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v)
 {

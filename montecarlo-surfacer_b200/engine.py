@@ -87,6 +87,8 @@ def load_library():
         "smcb_broadcast_positions": [P, P],
         "smcb_set_rng": [P, C.c_uint64, C.c_uint32, C.c_uint64],
         "smcb_evaluate": [P, C.c_int] + [P] * 8,
+        "smcb_get_wall_virial": [P, P],
+        "smcb_obs_set_wall_virial": [P, C.c_int],
         "smcb_sweep_fed": [P, C.c_int, C.c_int, P, P, P, P],
         "smcb_sweep": [P, C.c_int, C.c_int],
         "smcb_sweep_traced": [P, C.c_int, C.c_int, P, P, P, P, P],
@@ -241,6 +243,15 @@ class Engine:
                                         _ptr(g("f_wall")), _ptr(out["U_lj"]), _ptr(out["U_wall"]),
                                         _ptr(out["vir_lj"]), _ptr(out["vir_wall_ref"])))
         return out
+
+    def wall_virial(self):
+        """chain sums of the wall virial as the reference meant it (after evaluate() or gather())"""
+        v = np.empty(self.C)
+        self._ck(self.lib.smcb_get_wall_virial(self._h, _ptr(v)))
+        return v
+
+    def obs_set_wall_virial(self, intended):
+        self._ck(self.lib.smcb_obs_set_wall_virial(self._h, int(bool(intended))))
 
     # -- the sweep ---------------------------------------------------------------
     def sweep_fed(self, displ, offset, u, mode=STRICT, want_accepted=False):

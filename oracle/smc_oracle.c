@@ -257,6 +257,38 @@ double orc_walls_pressure(const orc_sys *s, const double *r, const double *W)
     return -acc / (3 * s->L * s->L * s->Lz);
 }
 
+/* The wall virial sum the reference MEANT (no reference code: wallsPressure has the three defects listed above):
+ * per particle, distance to the nearer wall as in wallsEnergySingle (SMC.c:735-739, clamp included), the flat-wall
+ * term r dV/dr once, and every surface site inside the cutoff.  Returns the SUM (pressure = -sum / (3 L^2 Lz)). */
+double orc_walls_virial_intended(const orc_sys *s, const double *r, const double *W)
+{
+    if (!s->wall) return 0.0;
+    const int M = s->M;
+    const double dw = s->L / M;
+    double acc = 0.0;
+    for (int n = 0; n < s->N; n++) {
+        const double rz = r[3 * n + 2];
+        double dz = rz + s->Lz / 2;
+        dz = dz - s->Lz * rint(dz / s->Lz);
+        if (rz <= -s->Lz / 2.0) dz = 0.0001;
+        else if (rz >= s->Lz / 2) dz = -0.0001;
+        const double z6 = dz * dz * dz * dz * dz * dz;
+        acc += 24.0 * s->b0 / z6 - 48.0 * s->a0 / (z6 * z6);
+        for (int i = 0; i < M; i++)
+            for (int j = 0; j < M; j++) {
+                const int m = j + i * M;
+                const double dx = min_image(r[3 * n] - i * dw, s->L);
+                const double dy = min_image(r[3 * n + 1] - j * dw, s->L);
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                if (r2 < s->rc2) {
+                    const double r6 = r2 * r2 * r2;
+                    acc += 24.0 * W[2 * m + 1] / r6 - 48.0 * W[2 * m] / (r6 * r6);
+                }
+            }
+    }
+    return acc;
+}
+
 /* ------------------------------------------------------------ random input */
 
 /* matematicose.c:183-193.  `rnd` holds the rand() results in draw order; uses

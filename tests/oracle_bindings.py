@@ -61,6 +61,8 @@ class Oracle:
         L.orc_walls_energy.argtypes = [S, dptr, dptr]
         L.orc_walls_pressure.restype = C.c_double
         L.orc_walls_pressure.argtypes = [S, dptr, dptr]
+        L.orc_walls_virial_intended.restype = C.c_double
+        L.orc_walls_virial_intended.argtypes = [S, dptr, dptr]
         L.orc_box_muller.argtypes = [C.c_double, C.c_size_t, iptr, C.c_int, dptr]
         L.orc_sweep.argtypes = [S, dptr, dptr, dptr, C.c_double, C.c_double, dptr, C.c_longlong, dptr,
                                 C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p]
@@ -118,6 +120,9 @@ class Oracle:
 
     def walls_pressure(self, s, r, W):
         return self.lib.orc_walls_pressure(C.byref(s), r, W)
+
+    def walls_virial_intended(self, s, r, W):
+        return self.lib.orc_walls_virial_intended(C.byref(s), r, W)
 
     def box_muller(self, sigma, length, rnd):
         out = np.zeros(length)

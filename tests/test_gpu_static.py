@@ -122,3 +122,51 @@ def test_no_cpu_fallback_error_paths():
             eng.evaluate()
         info = eng.device_info()
         assert info["cc"][0] >= 10 and info["sm_count"] > 0
+
+
+def test_wall_virial_as_intended(orc):
+    """the corrected wall virial (no reference code - wallsPressure has three defects): the CUDA
+    value against the CPU restatement and against r dV/dr differentiated numerically term by term; the gathered
+    pressure moment switches between the reference's arithmetic and the corrected one"""
+    N, M = 108, 3
+    L, Lz = geom(N)
+    s = make_sys(N, M, L, Lz)
+    W = GOLDEN_W_M3.copy()
+    R = mixed_configs(N, L, Lz, 4, seed=9, orc=orc)
+    with smcb.Engine(4, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz), W)
+        eng.set_positions(R)
+        for mode in (smcb.STRICT, smcb.FAST):
+            ev = eng.evaluate(mode, per_particle=False)
+            vw = eng.wall_virial()
+            for c in range(4):
+                ref = orc.walls_virial_intended(s, R[c], W)
+                assert abs(vw[c] - ref) <= TOL * max(1.0, abs(ref)), (mode, c, vw[c], ref)
+        # independent check on one chain: sum of r dV/dr with dV/dr by central differences of each 12-6 term
+        c, tot, h = 2, 0.0, 1e-6
+        v12_6 = lambda a, b, r: 4.0 * (a / r ** 12 - b / r ** 6)
+        for n in range(N):
+            x, y, z = R[c][3 * n:3 * n + 3]
+            dz = z + Lz / 2
+            dz -= Lz * np.rint(dz / Lz)
+            tot += abs(dz) * (v12_6(s.a0, s.b0, abs(dz) + h) - v12_6(s.a0, s.b0, abs(dz) - h)) / (2 * h)
+            for i in range(M):
+                for j in range(M):
+                    dx = x - i * L / M; dx -= L * np.rint(dx / L)
+                    dy = y - j * L / M; dy -= L * np.rint(dy / L)
+                    r = np.sqrt(dx * dx + dy * dy + dz * dz)
+                    if r * r < 9.0:
+                        a, b = W[2 * (i * M + j)], W[2 * (i * M + j) + 1]
+                        tot += r * (v12_6(a, b, r + h) - v12_6(a, b, r - h)) / (2 * h)
+        assert abs(vw[c] - tot) <= 1e-6 * max(1.0, abs(tot))
+        # pressure moment of the gather: reference arithmetic by default, corrected on request
+        vol3 = 3 * L * L * Lz
+        eng.gather()
+        p_ref = eng.obs_get()[0]["sumP"]
+        eng.obs_reset()
+        eng.obs_set_wall_virial(True)
+        eng.gather()
+        p_int = eng.obs_get()[0]["sumP"]
+        ev = eng.evaluate(smcb.FAST, per_particle=False)
+        assert abs(p_ref - np.sum(-(ev["vir_lj"] + ev["vir_wall_ref"]) / vol3)) <= 1e-10 * max(1e-6, abs(p_ref))
+        assert abs(p_int - np.sum(-(ev["vir_lj"] + eng.wall_virial()) / vol3)) <= 1e-10 * max(1e-6, abs(p_int))
