@@ -182,3 +182,14 @@ def test_obs_allreduce_single_process_two_gpus():
     finally:
         for eng in engines:
             eng.close()
+
+
+def test_every_kernel_small_case_runs_clean():
+    """profiles/sanitize_case.py (written for compute-sanitizer, which is closed on this pool): every kernel and
+    mode on small inputs, in a fresh process, must finish without a CUDA error"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "profiles", "sanitize_case.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "sanitize case done" in r.stdout, r.stderr[-1500:]
