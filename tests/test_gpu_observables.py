@@ -193,3 +193,28 @@ def test_every_kernel_small_case_runs_clean():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "profiles", "sanitize_case.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "sanitize case done" in r.stdout, r.stderr[-1500:]
+
+
+def test_full_size_run_to_run_determinism():
+    """8192 chains x N=256 twice with the same streams: sweeps, all-particle steps and the gathered observable
+    block are bit-identical (a data race in the warp/block-synchronised shared-memory protocols would show here)"""
+    N, M = 256, 3
+    L, Lz = geom(N)
+    orc = Oracle()
+    R0, _ = orc.initialize_box(L, Lz, N)
+    runs = []
+    for _ in range(2):
+        with smcb.Engine(8192, N, M) as eng:
+            eng.set_params(smcb.default_params(L=L, Lz=Lz, T=1.1, A=1.1), GOLDEN_W_M3)
+            eng.broadcast_positions(R0)
+            eng.set_rng(777, 0, 0)
+            eng.sweep(6, smcb.FAST)
+            eng.gather()
+            Rs, Es = eng.get_positions().copy(), eng.chain_state()[0].copy()
+            eng.set_params(smcb.default_params(L=L, Lz=Lz, T=1.1, A=2e-4), GOLDEN_W_M3)
+            eng.step_allparticle(6, smcb.FAST)
+            eng.gather()
+            o = eng.obs_get()[0]
+            runs.append((Rs, Es, eng.get_positions().copy(), eng.chain_state()[0].copy(), o["D"].copy(), o["sumE"], o["sumP"]))
+    for a, b in zip(runs[0], runs[1]):
+        np.testing.assert_array_equal(a, b)
