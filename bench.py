@@ -53,11 +53,12 @@ def parse():
     ap.add_argument("--sweeps-per-step", type=int, default=40)
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--kernel", default="sweep", choices=["sweep", "allparticle"])
-    ap.add_argument("--workload", default="batched", choices=["batched", "grid", "largeN"],
+    ap.add_argument("--workload", default="batched", choices=["batched", "bulk", "grid", "largeN"],
                     help="batched: 8192 chains x N=256 per GPU (configs[2], the headline); grid: 65536 chains in total on a "
                          "16 T x 4 Lz x 4 wall-strength grid x 256 replicas, sharded over the GPUs, one observable group per "
                          "grid point (configs[3]); largeN: 256 chains x N=4096 in total, sharded over the GPUs (configs[4], "
-                         "all-particle kernel with thread-block clusters)")
+                         "all-particle kernel with thread-block clusters); bulk: 8192 chains x N=108 per GPU, 3-D periodic, "
+                         "rho*=0.5, T*=1.0, cutoff L/2 (configs[0], the SMC_noMPI_noWall geometry)")
     ap.add_argument("--largeN-sweep", action="store_true",
                     help="largeN workload with the reference's sweep (block-per-chain kernel, N > 512) instead of the all-particle step")
     ap.add_argument("--start", default="lattice", choices=["lattice", "droplet"],
@@ -244,6 +245,9 @@ def main():
         N, args.kernel = 4096, ("sweep" if args.largeN_sweep else "allparticle")
         Cn = args.chains or smcb.shard_chains(256, world, rank).nchains      # --chains 32 emulates one rank of 8
         total_largeN = float(world) * Cn if args.chains else 256.0
+    bulk = args.workload == "bulk"
+    if bulk:                                        # configs[0]: SMC_noMPI_noWall.c:74-143 geometry, fcc start (its :359-394)
+        N = 108
     grid = None
     if args.workload == "grid":                     # configs[3]: the T / density / wall grid the MPI ranks used to split
         total_grid = (args.chains * world) if args.chains else 65536
@@ -260,14 +264,18 @@ def main():
 
     # start lattice of initializeBox(33, 240, 256) (SMC.c:413-465): 4x4x4 fcc cells, a = 8.25, shifted a/4
     # (N=4096: 16x16x4 cells, a = 33/16 - the reference's own generator is invalid there)
-    nxy, nz = (4, 4) if N == 256 else (16, 4)
-    a = L_BOX / nxy
+    nxy, nz = (4, 4) if N == 256 else ((3, 3) if N == 108 else (16, 4))
+    Lb = (108 / 0.5) ** (1.0 / 3.0)                 # bulk box: rho* = 0.5
+    a = (Lb if bulk else L_BOX) / nxy
     cells = np.array([(i, j, k) for i in range(nxy) for j in range(nxy) for k in range(nz)], dtype=float)
     basis = np.array([[0, 0, 0], [.5, .5, 0], [.5, 0, .5], [0, .5, .5]])
     X = (cells[:, None, :] + basis[None, :, :]).reshape(-1, 3) * a + a / 4
     Pz = LZ_BOX - LZ_BOX / 20.0
-    X[:, :2] -= L_BOX * np.rint(X[:, :2] / L_BOX)
-    X[:, 2] -= Pz * np.rint(X[:, 2] / Pz)
+    if bulk:
+        X -= Lb * np.rint(X / Lb)
+    else:
+        X[:, :2] -= L_BOX * np.rint(X[:, :2] / L_BOX)
+        X[:, 2] -= Pz * np.rint(X[:, 2] / Pz)
     R0 = X.reshape(-1)
     if args.start == "droplet":
         nzl = 4 if N <= 512 else 8
@@ -287,6 +295,10 @@ def main():
         Wt = np.concatenate([GOLDEN_W_M3 * (ym / 3.0) for ym in (2.0, 8.0 / 3.0, 10.0 / 3.0, 4.0)])
         eng.set_params(params, Wt, ngroups=ngroups)
         chain0 = shard.chain0
+    elif bulk:
+        A = 0.01 if args.kernel == "sweep" else 1e-4      # a liquid: the prototype's own A is 4e-8 (SMC_noMPI_noWall.c:192)
+        eng.set_params(smcb.default_params(L=Lb, Lz=Lb, T=1.0, A=A, rc2=Lb * Lb / 4, flags=smcb.PERIODIC_Z), None, ngroups=1)
+        chain0 = rank * Cn
     else:
         eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=A), GOLDEN_W_M3, ngroups=1)
         chain0 = rank * Cn
@@ -360,7 +372,7 @@ def main():
         dev_ms = smcb.max_over_ranks(k_tot + g_tot + c_tot, device="cuda")
         k_max = smcb.max_over_ranks(k_tot, device="cuda")
         unit_pairs = pairs_per_sweep(N) if kernel == "sweep" else float(N) * (N - 1)
-        total_chains = float(world) * Cn if args.workload == "batched" else (float(grid[4]) if grid else total_largeN)
+        total_chains = float(world) * Cn if args.workload in ("batched", "bulk") else (float(grid[4]) if grid else total_largeN)
         chain_steps = total_chains * S * nsteps
         flops = FLOPS_PAIR * pairs_tot + FLOPS_INCUT * pairs_cut
         return {"value": chain_steps * unit_pairs / (dev_ms * 1e-3), "chain_steps_per_s": chain_steps / (dev_ms * 1e-3),
@@ -399,7 +411,7 @@ def main():
             e2e_step()
         barrier()
         te = smcb.max_over_ranks(time.perf_counter() - t0, device="cuda")
-        total_chains = float(world) * Cn if args.workload == "batched" else (float(grid[4]) if grid else total_largeN)
+        total_chains = float(world) * Cn if args.workload in ("batched", "bulk") else (float(grid[4]) if grid else total_largeN)
         e2e = {"value": total_chains * S * nsteps_e2e * main["unit_pairs"] / te, "unit": "pair-interactions/s",
                "chain_steps_per_s": total_chains * S * nsteps_e2e / te, "steps": nsteps_e2e,
                "h2d_bytes_per_step": int(Cn * 3 * N * 8), "d2h_bytes_per_step": int(Cn * 3 * N * 8 + Cn * 24),
@@ -441,14 +453,16 @@ def main():
             "chain_steps_per_s": main["chain_steps_per_s"],
             "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": main["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak" if args.workload == "batched" or (grid and args.chains) else "strong", "vs_baseline": None,
+            "scaling": "weak" if args.workload in ("batched", "bulk") or (grid and args.chains) else "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": (f"{Cn} chains/GPU x N={N} with wall (BASELINE configs[2])" if args.workload == "batched"
+                                    else f"{Cn} chains/GPU x N={N} bulk, 3-D periodic, rho*=0.5, T*=1.0 (BASELINE configs[0] geometry)" if bulk
                                     else f"{grid[4]} chains x N={N} on a 16 T x 4 Lz x 4 wall grid x replicas (BASELINE configs[3]), "
                                          f"{Cn} on this rank, {len(grid[1]) * len(grid[2]) * len(grid[3])} observable groups all-reduced"
                                     if grid else f"{int(total_largeN)} chains x N={N} with wall in total (BASELINE configs[4]), {Cn} on this rank")
                                    + f", {args.kernel} kernel, {args.mode}",
-                       "chains_per_gpu": Cn, "N": N, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": A,
+                       "chains_per_gpu": Cn, "N": N, "M": M_SITES, "L": Lb if bulk else L_BOX, "Lz": Lb if bulk else LZ_BOX,
+                       "T": 1.0 if bulk else TEMP, "A": A,
                        "sweeps_per_step": S, "start": ("initializeBox fcc lattice" if args.start == "lattice" else "condensed droplet on the wall") + " + warm-up steps",
                        "l2": "flushed between timed steps (256 MB write)", "rng": "Philox4x32-10",
                        "parallelism": f"chains sharded x{world}, NCCL all-reduce of the observable block only"},
