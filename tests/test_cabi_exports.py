@@ -38,3 +38,24 @@ def test_no_device_means_error_not_fallback():
         assert rc == -3 and not h.value                      # SMCB_ERR_NODEVICE
         assert b"no CPU path" in lib.smcb_last_error()
     assert lib.smcb_create(ctypes.byref(h), 0, 0, 32, 3) == -1   # SMCB_ERR_ARG before any device work
+
+
+def test_dropin_exports_the_reference_api():
+    """the drop-in library (the reference's SMC.h API on libsmcb200, built by tests/dropin/Makefile) defines every
+    function the reference's SMC.h:92-121 and matematicose.h:6-28 declare; no GPU needed to check that"""
+    so = os.path.join(ROOT, "tests", "dropin", "_build", "libdropin_N108_M3.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "dropin")], check=True, capture_output=True)
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    defined = {ln.split()[-1] for ln in syms.splitlines() if ln.strip()}
+    smc_h = ["sMC", "vecBoxMuller", "shiftSystem", "shiftSystem2D", "shiftSystem3D", "createZRange", "initializeWalls",
+             "initializeBox", "oneParticleMoves", "energySingle", "forceSingle", "forces", "energy", "pressure", "wallsEnergy",
+             "wallsEnergySingle", "wallsForce", "wallsPressure", "localDensityAndMobility", "localDensityAndMobility_nonuniz",
+             "clusterAnalysis", "boundsCheck", "simple_acf", "fft_acf", "variance_corr"]
+    mat_h = ["isPicoEqual", "pointwise", "double_max_index", "double_min_index", "sum", "intsum", "mean", "intmean", "variance",
+             "zeros", "elforel", "isApproxEqual", "zerosecant", "secant", "findzero_last", "fast_bessel", "der3", "der5", "der5_c",
+             "simpson_integral", "grad_descent_1D", "stochastic_grad_descent_1D"]
+    missing = [f for f in smc_h + mat_h if f not in defined]
+    assert not missing, missing
+    needed = subprocess.run(["objdump", "-p", so], capture_output=True, text=True).stdout
+    assert "libsmcb200.so" in needed and "fftw" not in needed.lower()
