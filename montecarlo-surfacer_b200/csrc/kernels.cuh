@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
 
 }  // namespace smcb
 #include "sweep_cached.cuh"
+#include "sweep_spec.cuh"
 #include "allparticle_fast.cuh"
 #include "sweep_block.cuh"
 namespace smcb {

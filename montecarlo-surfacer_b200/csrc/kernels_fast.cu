@@ -1,6 +1,7 @@
 // kernels_fast.cu — FAST instantiations (FMA contraction on) plus the kernels
 // that have no strict/fast distinction (gather, layout transposes, DFMA peak).
 #include <cstdlib>
+#include <cstring>
 #define SMCB_MISC_KERNELS
 #include "launch.h"
 #define SMCB_TU_IS_STRICT 0

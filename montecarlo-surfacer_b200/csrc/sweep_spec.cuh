@@ -1,0 +1,472 @@
+// sweep_spec.cuh — the FAST sweep kernel, segment-speculative variant (oneParticleMoves, SMC.c:278-351).
+//
+// Same Markov chain as k_sweep_cached (same proposal, acceptance expression, visiting order and random inputs,
+// same caches, same packed-FP32 superset screen with exact FP64 terms for the hits).  k_sweep_cached resolves the
+// 32 trials of a segment one after the other: screen, vote, branch, and - for every trial that finds a partner
+// (~30 % of the trials of the benchmark gas) - a 560-instruction warp-wide general path for ONE pair.  That serial
+// chain is what bounds it (profiles/r01: 3 warps per scheduler, 59 % issue, one trial per 1160 cycles).
+//
+// Here the whole segment is evaluated LANE-PARALLEL against the state at the start of the segment:
+//   phase 1  lane t prepares trial t (random inputs, proposal from the cached force, flat-wall terms)    [as before]
+//   phase 2  the 32 proposals are screened against all K slots in one pipelined loop (independent iterations, two
+//            trials in flight).  Lane t keeps, for ITS trial: which lanes found hits (the hit masks go to a 32x32
+//            table in shared memory), which of the segment's own particles are in range of its proposal (po), and
+//            which of the other PROPOSALS are (pp, from a proposal-against-proposal test in the same loop)
+//   phase 3  lane t evaluates the exact FP64 pair terms of its own trial's partners (0-1 of them in the gas: a
+//            short divergent loop), adds the flat wall, and decides its trial completely (SMC.c:319-335)
+//   phase 4  the warp walks only the trials that need work, in visiting order: accepted ones are committed by
+//            their owner lane (position, caches, the one partner's caches, Newton's third law); a trial whose
+//            inputs were changed by an earlier accepted trial of the segment - its cached force (dirty), or the set
+//            of particles in range of its proposal ((pp | po) & accepted) - or that is near the surface or has
+//            several partners, is redone on the warp-wide general path of k_sweep_cached.  Rejected trials with
+//            valid speculation cost nothing in phase 4.
+// A trial's speculation is valid exactly when nothing it read has changed since the start of the segment, so the
+// results are those of the sequential sweep (tests: accept flags identical to the oracle's, positions and energies
+// within 1e-12 teacher-forced; cache consistency after many sweeps).
+//
+// Dense states (a droplet on the wall: 30-80 partners each, every accepted move dirties a quarter of the segment)
+// make the speculation worthless; a segment whose particles average more than two partners skips phases 2-3 and
+// sends every trial to the general path (the behaviour of k_sweep_cached).
+#pragma once
+
+namespace smcb {
+
+template <int K> struct HitMaskT { typedef unsigned char type; };
+template <> struct HitMaskT<16> { typedef unsigned short type; };
+
+template <int K>
+struct SpecSmem {
+    static constexpr int NS = 32 * K;
+    static __host__ __device__ size_t bytes(int MMpad)
+    {
+        return ChainSmem::bytes(NS, MMpad) + (size_t)32 * 32 * sizeof(typename HitMaskT<K>::type);
+    }
+};
+
+#ifndef SMCB_SPEC_MINB
+#define SMCB_SPEC_MINB 10
+#endif
+
+template <int K, bool FED, bool PZ>
+__device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepArgs &a)
+{
+    typedef typename HitMaskT<K>::type HM;
+    const int lane = threadIdx.x, chain = blockIdx.x;
+    const int N = d.N, Npad = d.Npad;
+    const int MM = d.M * d.M, MMpad = (MM + 3) & ~3;
+    extern __shared__ double sm[];
+    ChainSmem s;
+    s.carve(sm, 32 * K, MMpad);
+    HM *hm = reinterpret_cast<HM *>(s.site + 4 * MMpad);      // [trial][lane]: the lane's hit mask for the trial's proposal
+    const smcb_chain_params &cp = chain_params(d, chain);
+    const Box b = make_box(cp, d.M, d.step_scale);
+    const double *W = d.W + (size_t)cp.wall * 2 * MM;
+    double *P = d.pos + (size_t)chain * 3 * Npad;
+
+    Slots<K> q;
+    if (K & 1) q.set(K, 0.f, 0.f, 3.0e18f);              // pad slot of an odd K: never within the cutoff
+    unsigned validmask = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int j = lane + 32 * k;
+        const bool in = j < N;
+        const double X = in ? P[j] : 0.0, Y = in ? P[Npad + j] : 0.0, Z = in ? P[2 * Npad + j] : 0.0;
+        if (j < Npad) { s.x[j] = X; s.y[j] = Y; s.z[j] = Z; }
+        q.set(k, (float)(X * b.invL), (float)(Y * b.invL), (float)(Z * b.invL));
+        if (in) validmask |= 1u << k;
+    }
+    if (b.wall) {
+        const double dw = b.L / d.M;
+        for (int m = lane; m < MM; m += 32) {
+            const int si = m / d.M, sj = m - si * d.M;
+            s.site[m] = si * dw; s.site[MMpad + m] = sj * dw;
+            s.site[2 * MMpad + m] = W[2 * m]; s.site[3 * MMpad + m] = W[2 * m + 1];
+        }
+    }
+    __syncwarp();
+    const ScreenConsts sc = make_screen(b);
+
+    // ---- rebuild the caches from the positions ------------------------------------
+    for (int n = 0; n < N; n++) {
+        const unsigned okmask = validmask & ~(((n & 31) == lane) ? (1u << (n >> 5)) : 0u);
+        double U, Fx, Fy, Fz;
+        unsigned in;
+        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], q, U, Fx, Fy, Fz, in);
+        const int cntn = __reduce_add_sync(FULL, __popc(in));
+        if (lane == 0) { s.ce[n] = U; s.cfx[n] = Fx; s.cfy[n] = Fy; s.cfz[n] = Fz; s.nb[n] = (unsigned short)cntn; }
+    }
+    __syncwarp();
+
+    const double AoT = b.A / b.T;
+    const double sigma = sqrt(2.0 * b.A);            // vecBoxMuller(sqrt(2.0*A), ...)  SMC.c:284
+    const double quarterAoT = 0.25 * AoT, invT = 1.0 / b.T;
+    double E = d.E[chain];
+    double dE = 0.0;                                 // per-lane share of the running energy (owner-committed trials)
+    int nacc = 0;
+    unsigned cnt = 0;                                // per-lane, < 2^32 per launch
+    const RngId id{a.rng.k0, a.rng.k1, a.rng.chain0 + (uint32_t)chain};
+
+    // physical register slot 0 always holds the slot being visited (see k_sweep_cached): `rot` = logical slot at physical 0
+    int rot = 0;
+    auto rotate = [&]() {
+        if (K > 1) {
+            float tx, ty, tz, ux, uy, uz;
+            q.get(0, tx, ty, tz);
+#pragma unroll
+            for (int k = 0; k + 1 < K; k++) { q.get(k + 1, ux, uy, uz); q.set(k, ux, uy, uz); }
+            q.set(K - 1, tx, ty, tz);
+            validmask = (validmask >> 1) | ((validmask & 1u) << (K - 1));
+            rot = (rot + 1 == K) ? 0 : rot + 1;
+        }
+    };
+    auto particle_of = [&](int k) { int sl = k + rot; if (sl >= K) sl -= K; return lane + 32 * sl; };
+
+    for (int sw = 0; sw < a.nsweeps; sw++) {
+        const unsigned long long step = a.rng.step0 + (unsigned long long)sw;
+        const size_t sci = (size_t)sw * d.C + chain;
+        const int nacc0 = nacc;
+        long long offset;                              // int offset = rand();  SMC.c:290
+        if (FED) {
+            offset = a.offset[sci];
+        } else {
+            uint32_t o; double unused;
+            rng_step_scalars(id, step, o, unused);
+            offset = o;
+        }
+        const int off = (int)(offset % N);             // first particle of the sweep: n = (nn+offset)%N, SMC.c:294
+        const int slot0 = off >> 5, t0 = off & 31;
+        while (rot != slot0) rotate();
+        // K+1 segments: [off .. end of its slot], the following slots cyclically, then [start of slot0 .. off-1]
+        for (int seg = 0; seg <= K; seg++) {
+            const int slot = rot;
+            const int tb = (seg == 0) ? t0 : 0;
+            int te = min(32, N - 32 * slot);            // particles of this slot that exist
+            if (seg == K) te = min(te, t0);
+            if (tb < te) {
+                // ================= phase 1: lane t prepares trial t (particle 32*slot+t) =================
+                const int nl = 32 * slot + lane;
+                const bool mine = lane >= tb && lane < te;
+                __syncwarp();                           // the previous segment is done with the staging area
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, lul = 0.0;
+                double p_qx = 0.0, p_qy = 0.0, p_qz = 0.0, p_ew = 0.0, p_fz = 0.0, p_dU = 0.0;
+                double pe = 0.0, pgx = 0.0, pgy = 0.0, pgz = 0.0;     // pair terms of the trial's one partner at the proposal
+                int pj = -1, p_np = 0, nb0 = 0;
+                bool p_bad = false, p_acc = false;      // bad: near the surface or several partners -> general path
+                float st_x = 0.f, st_y = 0.f, st_z = 3.0e18f;        // lanes without a trial: out of everybody's range
+                if (mine) {
+                    double ul;
+                    if (FED) {
+                        const double *dsp = a.displ + sci * 3 * N;
+                        g0 = dsp[3 * nl]; g1 = dsp[3 * nl + 1]; g2 = dsp[3 * nl + 2];
+                        int nn = nl - off;              // trial index in visiting order (u is per trial, SMC.c:335)
+                        if (nn < 0) nn += N;
+                        ul = a.u[sci * N + nn];
+                    } else {
+                        rng_particle_gauss_f32(id, step, (uint32_t)nl, g0, g1, g2);
+                        g0 *= sigma; g1 *= sigma; g2 *= sigma;
+                        ul = rng_particle_uniform(id, step, (uint32_t)nl);
+                    }
+                    lul = log(ul);                      // u < exp(x)  <=>  log(u) < x, evaluated lane-parallel
+                    const double dX = fma(s.cfx[nl], AoT, g0), dY = fma(s.cfy[nl], AoT, g1), dZ = fma(s.cfz[nl], AoT, g2);   // SMC.c:307-309
+                    p_qx = min_image<false>(s.x[nl] + dX, b.L, b.invL);                                    // SMC.c:311-316
+                    p_qy = min_image<false>(s.y[nl] + dY, b.L, b.invL);
+                    p_qz = s.z[nl] + dZ;
+                    if (PZ) p_qz = min_image<false>(p_qz, b.Lz, b.invLz);
+                    if (b.wall) {
+                        const double dzw = wall_dz<false>(b, p_qz);
+                        p_bad = dzw * dzw < b.rc2;      // surface sites in range: the general path sums them
+                        add_zwall(b, dzw, p_ew, p_fz);
+                    }
+                    nb0 = s.nb[nl];
+                    st_x = (float)(p_qx * b.invL); st_y = (float)(p_qy * b.invL); st_z = (float)(p_qz * b.invL);
+                }
+                s.stage[lane] = st_x; s.stage[32 + lane] = st_y; s.stage[64 + lane] = st_z;
+                const bool lite = __reduce_add_sync(FULL, (unsigned)nb0) > 2u * (unsigned)(te - tb);   // dense segment: no speculation
+                __syncwarp();
+
+                unsigned my_hb = 0, my_po = 0, my_pp = 0;
+                if (!lite) {
+                    // ================= phase 2: the segment's proposals against all slots, and against each other ==========
+                    const float MGs = 12582912.f;
+                    for (int t2 = tb & ~1; t2 < te; t2 += 2) {
+                        const float2 sx2 = *reinterpret_cast<const float2 *>(s.stage + t2);
+                        const float2 sy2 = *reinterpret_cast<const float2 *>(s.stage + 32 + t2);
+                        const float2 sz2 = *reinterpret_cast<const float2 *>(s.stage + 64 + t2);
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int t = t2 + h;
+                            const float ax = h ? sx2.y : sx2.x, ay = h ? sy2.y : sy2.x, az = h ? sz2.y : sz2.x;
+                            const unsigned m = screen_slots<K, PZ>(sc, ax, ay, az, q) & validmask & ~((lane == t) ? 1u : 0u);
+                            const unsigned hb = __ballot_sync(FULL, m != 0);
+                            const unsigned po = __ballot_sync(FULL, (m & 1u) != 0);
+                            if (m) hm[t * 32 + lane] = (HM)m;
+                            float dx = ax - st_x, dy = ay - st_y, dz = az - st_z;
+                            dx -= (dx + MGs) - MGs;
+                            dy -= (dy + MGs) - MGs;
+                            if (PZ) dz = fmaf((dz * sc.inv_zper + MGs) - MGs, -sc.zper, dz);
+                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            const unsigned pp = __ballot_sync(FULL, (r2 < sc.rc2s) && lane != t);
+                            if (lane == t) { my_hb = hb; my_po = po; my_pp = pp; }
+                        }
+                    }
+                    __syncwarp();
+                    // ================= phase 3: lane t evaluates and decides its own trial =================
+                    if (mine && !p_bad) {
+                        unsigned hb = my_hb;
+                        while (hb) {
+                            const int l = __ffs(hb) - 1;
+                            hb &= hb - 1;
+                            unsigned m = hm[lane * 32 + l];
+                            while (m) {
+                                const int k = __ffs(m) - 1;
+                                m &= m - 1;
+                                int sl = k + rot;
+                                if (sl >= K) sl -= K;
+                                const int j = l + 32 * sl;
+                                double et, hx, hy, hz;
+                                if (pair_exact(b, p_qx, p_qy, p_qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
+                                    pe = et; pgx = hx; pgy = hy; pgz = hz; pj = j;
+                                    p_np++;
+                                }
+                            }
+                        }
+                        if (p_np > 1) {
+                            p_bad = true;
+                        } else {
+                            const double Um = s.ce[nl], Fmx = s.cfx[nl], Fmy = s.cfy[nl], Fmz = s.cfz[nl];   // SMC.c:300-304, cached
+                            const double dX = fma(Fmx, AoT, g0), dY = fma(Fmy, AoT, g1), dZ = fma(Fmz, AoT, g2);
+                            const double Un = 4.0 * (pe + p_ew), Fnz = pgz + p_fz;                            // SMC.c:319-321
+                            const double f2 = fma(pgx, pgx, fma(pgy, pgy, Fnz * Fnz)) - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
+                            const double dr = fma(dX, pgx + Fmx, fma(dY, pgy + Fmy, dZ * (Fnz + Fmz)));
+                            p_dU = Un - Um;
+                            const double xarg = -(p_dU + 0.5 * dr + f2 * quarterAoT) * invT;                  // SMC.c:326-329
+                            p_acc = (lul < xarg) && (xarg > -745.1332191019411);
+                        }
+                    }
+                }
+
+                // ================= phase 4: resolve in visiting order =================
+                unsigned A = 0;                          // trials of this segment accepted so far
+                unsigned genmask = 0;                    // trials that went through the general path
+                unsigned dirty = 0;                      // particles of the visited slot whose caches were touched by an accepted trial
+                // the partners of particle m's CURRENT (old) position lose their pair terms with m (force on j from m = -g d);
+                // returns whether a particle of the slot being visited (physical slot 0) was touched
+                auto drop_old_partners = [&](int m, unsigned okm) -> bool {
+                    const double px = s.x[m], py = s.y[m], pz = s.z[m];
+                    unsigned ho = screen_slots<K, PZ>(sc, (float)(px * b.invL), (float)(py * b.invL), (float)(pz * b.invL), q) & okm;
+                    bool touched = false;
+                    while (ho) {
+                        const int k = __ffs(ho) - 1;
+                        ho &= ho - 1;
+                        const int j = particle_of(k);
+                        double et, hx, hy, hz;
+                        if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
+                            s.ce[j] -= 4.0 * et; s.cfx[j] += hx; s.cfy[j] += hy; s.cfz[j] += hz;
+                            s.nb[j] -= 1;
+                            touched |= (k == 0);
+                        }
+                    }
+                    return touched;
+                };
+                int cur = tb;
+                while (cur < te) {
+                    const bool pending = mine && lane >= cur;
+                    const bool conf = pending && (lite || p_bad || ((dirty >> lane) & 1u) || (((my_pp | my_po) & A) != 0u));
+                    const unsigned confb = __ballot_sync(FULL, conf);
+                    const unsigned cand = confb | __ballot_sync(FULL, pending && p_acc);
+                    if (cand == 0u) break;
+                    const int t = __ffs(cand) - 1;
+                    cur = t + 1;
+                    const int n = 32 * slot + t;
+                    const unsigned okmask = validmask & ~((lane == t) ? 1u : 0u);
+                    const int nbm = s.nb[n];
+                    if (!((confb >> t) & 1u)) {
+                        // ---- the speculation of trial t stands and it accepts: its owner commits it
+                        if (nbm) {                       // the old partners forget this particle
+                            __syncwarp();
+                            dirty |= __ballot_sync(FULL, drop_old_partners(n, okmask));
+                            __syncwarp();
+                        }
+                        if (lane == t) {
+                            if (pj >= 0) {               // the one new partner gains the pair terms (force on j from n = -g d)
+                                s.ce[pj] += 4.0 * pe; s.cfx[pj] -= pgx; s.cfy[pj] -= pgy; s.cfz[pj] -= pgz;
+                                s.nb[pj] += 1;
+                            }
+                            s.x[n] = p_qx; s.y[n] = p_qy; s.z[n] = p_qz;
+                            s.ce[n] = 4.0 * (pe + p_ew); s.cfx[n] = pgx; s.cfy[n] = pgy; s.cfz[n] = pgz + p_fz;
+                            s.nb[n] = (unsigned short)(pj >= 0 ? 1 : 0);
+                            q.set(0, st_x, st_y, st_z);
+                            dE += p_dU;                 // SMC.c:341, summed per lane, reduced at the end of the sweep
+                        }
+                        const int pjt = __shfl_sync(FULL, pj, t);
+                        if (pjt >= 0 && (pjt >> 5) == slot) dirty |= 1u << (pjt & 31);
+                        A |= 1u << t;
+                        nacc++;
+                        __syncwarp();
+                        continue;
+                    }
+                    // ---- general path: trial t is evaluated by the whole warp against the CURRENT state
+                    genmask |= 1u << t;
+                    const bool reuse = !((dirty >> t) & 1u);        // its cached force is untouched: the proposal of phase 1 stands
+                    __syncwarp();
+                    const double dX = fma(s.cfx[n], AoT, __shfl_sync(FULL, g0, t));
+                    const double dY = fma(s.cfy[n], AoT, __shfl_sync(FULL, g1, t));
+                    const double dZ = fma(s.cfz[n], AoT, __shfl_sync(FULL, g2, t));
+                    double qx, qy, qz, ew = 0.0, fzw = 0.0, dzw = 0.0;
+                    float qsx, qsy, qsz;
+                    bool near = false;
+                    if (reuse) {
+                        qx = __shfl_sync(FULL, p_qx, t); qy = __shfl_sync(FULL, p_qy, t); qz = __shfl_sync(FULL, p_qz, t);
+                        ew = __shfl_sync(FULL, p_ew, t); fzw = __shfl_sync(FULL, p_fz, t);
+                        qsx = s.stage[t]; qsy = s.stage[32 + t]; qsz = s.stage[64 + t];
+                        if (b.wall) { dzw = wall_dz<false>(b, qz); near = dzw * dzw < b.rc2; }
+                    } else {
+                        qx = min_image<false>(s.x[n] + dX, b.L, b.invL);
+                        qy = min_image<false>(s.y[n] + dY, b.L, b.invL);
+                        qz = s.z[n] + dZ;
+                        if (PZ) qz = min_image<false>(qz, b.Lz, b.invLz);
+                        qsx = (float)(qx * b.invL); qsy = (float)(qy * b.invL); qsz = (float)(qz * b.invL);
+                        if (b.wall) {                    // flat wall at the proposal: uniform, no cutoff
+                            dzw = wall_dz<false>(b, qz);
+                            near = dzw * dzw < b.rc2;
+                            add_zwall(b, dzw, ew, fzw);
+                        }
+                    }
+                    unsigned hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
+
+                    double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+                    double le = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
+                    unsigned in_new = 0;
+                    const bool work = __any_sync(FULL, hits_new != 0) || near;
+                    if (work) {
+                        while (hits_new) {
+                            const int k = __ffs(hits_new) - 1;
+                            hits_new &= hits_new - 1;
+                            const int j = particle_of(k);
+                            double et, hx, hy, hz;
+                            if (pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
+                                e += et; fx += hx; fy += hy; fz += hz;
+                                in_new |= 1u << k;
+                            }
+                        }
+                        // a lane with exactly one partner (the usual case) holds that pair's terms in e, fx, fy, fz:
+                        // keep them for the partner's cache update instead of evaluating the pair again
+                        le = e; lx = fx; ly = fy; lz = fz;
+                        if (near) add_sites(b, s, lane, MMpad, qx, qy, dzw, e, fx, fy, fz);
+                        // Sum over the warp.  Usually one or two lanes hold a partner: their four partial sums are
+                        // fetched with independent shuffles instead of the butterfly; lane order is fixed either way.
+                        unsigned holders = __ballot_sync(FULL, in_new != 0 || (near && lane < MM));
+                        if (__popc(holders) <= 2) {
+                            double te_ = 0.0, tx = 0.0, ty = 0.0, tz = 0.0;
+                            while (holders) {
+                                const int src = __ffs(holders) - 1;
+                                holders &= holders - 1;
+                                te_ += __shfl_sync(FULL, e, src); tx += __shfl_sync(FULL, fx, src);
+                                ty += __shfl_sync(FULL, fy, src); tz += __shfl_sync(FULL, fz, src);
+                            }
+                            e = te_; fx = tx; fy = ty; fz = tz;
+                        } else {
+                            warp_sum4(lane, e, fx, fy, fz);
+                        }
+                    }
+                    const double Un = 4.0 * (e + ew), Fnx = fx, Fny = fy, Fnz = fz + fzw;                 // SMC.c:319-321
+
+                    // SMC.c:326-335: accept iff u < exp(-(Un-Um + d.(Fn+Fm)/2 + (Fn^2-Fm^2) A/(4T))/T)
+                    const double Um = s.ce[n], Fmx = s.cfx[n], Fmy = s.cfy[n], Fmz = s.cfz[n];           // SMC.c:300-304, cached
+                    const double f2 = fma(Fnx, Fnx, fma(Fny, Fny, Fnz * Fnz)) - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
+                    const double dr = fma(dX, Fnx + Fmx, fma(dY, Fny + Fmy, dZ * (Fnz + Fmz)));
+                    const double xarg = -((Un - Um) + 0.5 * dr + f2 * quarterAoT) * invT;
+                    const double lu = __shfl_sync(FULL, lul, t);
+                    const bool acc = (lu < xarg) && (xarg > -745.1332191019411);    // exp underflows to 0 below that
+                    cnt += __popc(in_new) + (lane == 0 ? nbm : 0);   // partners at the new + at the old position
+                    if (acc) {
+                        // partners lose the old pair terms and gain the new ones (force on j from n = -g d)
+                        bool touched = false;           // physical slot 0 = the slot being visited: its speculation is void
+                        if (nbm) touched = drop_old_partners(n, okmask);
+                        int nbn = 0;
+                        if (work) {
+                            unsigned hn = in_new;
+                            const bool single = __popc(in_new) == 1 && !(near && lane < MM);   // le.. are that one pair's terms
+                            while (hn) {
+                                const int k = __ffs(hn) - 1;
+                                hn &= hn - 1;
+                                const int j = particle_of(k);
+                                double et = le, hx = lx, hy = ly, hz = lz;
+                                if (!single) pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz);
+                                s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
+                                s.nb[j] += 1;
+                                touched |= (k == 0);
+                            }
+                            nbn = __reduce_add_sync(FULL, __popc(in_new));
+                        }
+                        dirty |= __ballot_sync(FULL, touched);
+                        __syncwarp();                    // partner updates read the old position of n: order before overwriting it
+                        if (lane == t) {                 // the owner: physical slot 0 is the visited slot
+                            s.x[n] = qx; s.y[n] = qy; s.z[n] = qz;
+                            s.ce[n] = Un; s.cfx[n] = Fnx; s.cfy[n] = Fny; s.cfz[n] = Fnz;
+                            s.nb[n] = (unsigned short)nbn;
+                            q.set(0, qsx, qsy, qsz);
+                        }
+                        E += Un - Um;                   // SMC.c:341
+                        nacc++;
+                        A |= 1u << t;
+                        if (!lite && pending && lane > t) {   // pending proposals against the position n actually moved to
+                            float dx = st_x - qsx, dy = st_y - qsy, dz = st_z - qsz;
+                            const float MGs = 12582912.f;
+                            dx -= (dx + MGs) - MGs;
+                            dy -= (dy + MGs) - MGs;
+                            if (PZ) dz = fmaf((dz * sc.inv_zper + MGs) - MGs, -sc.zper, dz);
+                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            my_pp = (r2 < sc.rc2s) ? (my_pp | (1u << t)) : (my_pp & ~(1u << t));
+                        }
+                    }
+                    __syncwarp();
+                }
+                // in-cutoff pair statistics of the trials that never reached the general path (the reference evaluates them)
+                if (mine && !((genmask >> lane) & 1u)) cnt += (unsigned)(p_np + nb0);
+                if (FED && a.accepted != nullptr && mine) {
+                    int nn = nl - off;
+                    if (nn < 0) nn += N;
+                    a.accepted[sci * N + nn] = (unsigned char)((A >> lane) & 1u);
+                }
+            }
+            if (seg < K) rotate();
+        }
+        E += warp_sum(dE);
+        dE = 0.0;
+        if (a.trace_E != nullptr && lane == 0) { a.trace_E[sci] = E; a.trace_acc[sci] = nacc - nacc0; }
+    }
+
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) {               // the shared-memory mirror holds the exact positions
+        P[j] = s.x[j]; P[Npad + j] = s.y[j]; P[2 * Npad + j] = s.z[j];
+    }
+    if (a.cache_out) {                                  // test hook: the caches as they stand at the end
+        double *co = a.cache_out + (size_t)chain * 5 * Npad;
+        for (int j = lane; j < N; j += 32) {
+            co[j] = s.ce[j]; co[Npad + j] = s.cfx[j]; co[2 * Npad + j] = s.cfy[j]; co[3 * Npad + j] = s.cfz[j];
+            co[4 * Npad + j] = (double)s.nb[j];
+        }
+    }
+    unsigned long long tot = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+    if (lane == 0) {
+        d.E[chain] = E;
+        d.nacc[chain] += nacc;
+        d.ntri[chain] += (long long)a.nsweeps * N;
+        if (d.pair_counts) {
+            atomicAdd(d.pair_counts, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));
+            atomicAdd(d.pair_counts + 1, tot);
+        }
+    }
+}
+
+template <int K, bool FED>
+__global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SPEC_MINB : 8)) k_sweep_spec(DevChains d, SweepArgs a)
+{
+    if (chain_params(d, blockIdx.x).flags & SMCB_PERIODIC_Z) sweep_spec_body<K, FED, true>(d, a);
+    else sweep_spec_body<K, FED, false>(d, a);
+}
+
+}  // namespace smcb
