@@ -72,55 +72,6 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
     if (use_spec) err = fed ? go(k_sweep_spec<K, true>) : go(k_sweep_spec<K, false>);
     else          err = fed ? go(k_sweep_cached<K, true>) : go(k_sweep_cached<K, false>);
     if (err != cudaSuccess) return err;
-    int per = (d.N + parts - 1) / parts;
-    int threads = ((per + 31) / 32) * 32;
-    threads = threads > 512 ? 512 : (threads < 64 ? 64 : threads);
-    EvalFastArgs ea{parts, partials, tickets};
-    k_evaluate_fast<<<d.C * parts, threads, smem, st>>>(d, o, ea);
-    return cudaGetLastError();
-}
-#endif
-
-#if SMCB_TU_IS_STRICT
-cudaError_t SMCB_CAT(launch_evaluate_, SMCB_TU_SUFFIX)(const DevChains &d, const EvalOut &o, cudaStream_t st)
-{
-    const size_t smem = (size_t)(3 * d.Npad + 8 * 32) * sizeof(double);
-    auto kern = k_evaluate<SMCB_TU_STRICT>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    kern<<<d.C, eval_threads(d.N), smem, st>>>(d, o);
-    return cudaGetLastError();
-}
-#endif
-
-template <int K>
-static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
-{
-#if SMCB_TU_IS_STRICT
-    const size_t smem = (size_t)3 * d.Npad * sizeof(double);
-    if (fed) k_sweep<K, true, true><<<d.C, 32, smem, st>>>(d, a);
-    else     k_sweep<K, true, false><<<d.C, 32, smem, st>>>(d, a);
-#else
-    const int MMpad = (d.M * d.M + 3) & ~3;
-    // SMCB_SWEEP_KERNEL = spec (default: segment-speculative) | cached (first generation) | coop (compacted hit lists): A/B runs
-    static const int variant = [] {
-        const char *e = getenv("SMCB_SWEEP_KERNEL");
-        return !e ? 0 : (!strcmp(e, "cached") ? 1 : (!strcmp(e, "coop") ? 2 : 0));
-    }();
-    size_t smem = variant == 1 ? ChainSmem::bytes(32 * K, MMpad) : (variant == 2 ? CoopSmem<K>::bytes(MMpad) : SpecSmem<K>::bytes(MMpad));
-    if (const char *env = getenv("SMCB_SWEEP_SMEM_PAD")) smem += (size_t)atoi(env);     // occupancy experiments (profiles/)
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t err;
-    auto go = [&](auto kern) -> cudaError_t {
-        if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-        if ((err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)) != cudaSuccess) return err;
-        kern<<<d.C, 32, smem, st>>>(d, a);
-        return cudaSuccess;
-    };
-    if (variant == 1)      err = fed ? go(k_sweep_cached<K, true>) : go(k_sweep_cached<K, false>);
-    else if (variant == 2) err = fed ? go(k_sweep_coop<K, true>) : go(k_sweep_coop<K, false>);
-    else                   err = fed ? go(k_sweep_spec<K, true>) : go(k_sweep_spec<K, false>);
-    if (err != cudaSuccess) return err;
 #endif
     return cudaGetLastError();
 }
