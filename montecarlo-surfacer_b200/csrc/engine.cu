@@ -81,6 +81,7 @@ struct smcb_engine {
     float last_ms = 0.f;
     int last_launches = 0;
     unsigned long long last_pairs[2] = {0, 0};
+    int sweep_dense = 0;                    // the last FAST sweep launch found > 2 % of the pairs inside the cutoff
 
     DevChains chains()
     {
@@ -115,7 +116,7 @@ namespace {
 struct CkptHeader {
     char magic[8];                 // "SMCB200\0"
     uint32_t version, C, N, M, ngroups, nebins;
-    uint32_t chain0, pad_;
+    uint32_t chain0, pad_;            // pad_: the sweep kernel hint (sweep_dense)
     uint64_t seed, step;
     double step_scale, e_lo, e_hi;
     uint64_t n_counters, n_moments;
@@ -498,8 +499,10 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
     CK(cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     const DevChains d = e->chains();
+    a.dense_hint = e->sweep_dense;
     CK(mode == SMCB_STRICT ? launch_sweep_strict(fed, d, a, e->stream) : launch_sweep_fast(fed, d, a, e->stream));
     if ((rc = finish_timed(e, 1))) return rc;
+    if (mode == SMCB_FAST) e->sweep_dense = e->last_pairs[1] * 50ull > e->last_pairs[0] ? 1 : 0;
     if (fed && accepted) {
         CK(cudaMemcpyAsync(accepted, e->fed_acc.p, sc * e->N, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
@@ -803,7 +806,7 @@ int smcb_checkpoint_save(smcb_engine *e, const char *path)
     CkptHeader h{};
     memcpy(h.magic, "SMCB200", 8);
     h.version = 1; h.C = e->C; h.N = e->N; h.M = e->M; h.ngroups = e->ngroups; h.nebins = e->nebins;
-    h.chain0 = e->chain0; h.seed = e->seed; h.step = e->step; h.step_scale = e->step_scale;
+    h.chain0 = e->chain0; h.pad_ = (uint32_t)e->sweep_dense; h.seed = e->seed; h.step = e->step; h.step_scale = e->step_scale;
     h.e_lo = e->e_lo; h.e_hi = e->e_hi;
     h.n_counters = e->u64_per_group() * e->ngroups; h.n_moments = e->f64_per_group() * e->ngroups;
     std::vector<unsigned char> buf;
@@ -855,6 +858,7 @@ int smcb_checkpoint_load(smcb_engine *e, const char *path)
     if (w == -1) return fail(SMCB_ERR_CUDA, "checkpoint_load: device copy failed");
     if (w) return fail(SMCB_ERR_ARG, "checkpoint_load: %s is truncated", path);
     e->seed = h.seed; e->chain0 = h.chain0; e->step = h.step; e->step_scale = h.step_scale;
+    e->sweep_dense = h.pad_ == 1u ? 1 : 0;      // the resumed run launches the kernel the saved run would have launched next
     e->have_pos = true; e->energy_valid = true; e->forces_valid = false;
     return SMCB_OK;
 }

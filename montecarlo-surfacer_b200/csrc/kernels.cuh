@@ -55,6 +55,7 @@ struct SweepArgs {
     double *cache_out;         // test hook of the cached kernel, nullable: [C][5][Npad]
     double *trace_E;           // nullable [s][C]: running energy after every sweep (sMC's E[n+1], SMC.c:116,194)
     int *trace_acc;            // nullable [s][C]: accepted trials of every sweep (sMC's jj[n])
+    int dense_hint;            // host side only: 1 = the previous launch found > 2 % of the pairs inside the cutoff (condensed phase)
 };
 
 struct StepArgs {

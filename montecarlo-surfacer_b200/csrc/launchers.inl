@@ -57,8 +57,11 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
     else     k_sweep<K, true, false><<<d.C, 32, smem, st>>>(d, a);
 #else
     const int MMpad = (d.M * d.M + 3) & ~3;
-    // SMCB_SWEEP_KERNEL = cached (default) | spec (segment-speculative variant, sweep_spec.cuh): A/B runs
-    static const bool use_spec = [] { const char *e = getenv("SMCB_SWEEP_KERNEL"); return e && !strcmp(e, "spec"); }();
+    // Two FAST kernels: k_sweep_spec (segment-speculative, sweep_spec.cuh) for gas-like states, k_sweep_cached for condensed
+    // ones (every accepted move voids a quarter of a segment's speculation there).  The engine passes what the previous
+    // launch saw; SMCB_SWEEP_KERNEL = cached | spec pins one of them (A/B measurements).
+    static const int pin = [] { const char *e = getenv("SMCB_SWEEP_KERNEL"); return !e ? 0 : (!strcmp(e, "cached") ? 1 : (!strcmp(e, "spec") ? 2 : 0)); }();
+    const bool use_spec = pin ? pin == 2 : a.dense_hint != 1;
     size_t smem = use_spec ? SpecSmem<K>::bytes(MMpad) : ChainSmem::bytes(32 * K, MMpad);
     if (const char *env = getenv("SMCB_SWEEP_SMEM_PAD")) smem += (size_t)atoi(env);     // occupancy experiments (profiles/)
     if (smem > 227 * 1024) return cudaErrorInvalidValue;

@@ -39,7 +39,7 @@ struct SpecSmem {
     static constexpr int NS = 32 * K;
     static __host__ __device__ size_t bytes(int MMpad)
     {
-        return ChainSmem::bytes(NS, MMpad) + (size_t)32 * 32 * sizeof(typename HitMaskT<K>::type);
+        return ChainSmem::bytes(NS, MMpad) + (size_t)32 * 32 * sizeof(typename HitMaskT<K>::type) + 32 * sizeof(unsigned);
     }
 };
 
@@ -57,7 +57,8 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
     extern __shared__ double sm[];
     ChainSmem s;
     s.carve(sm, 32 * K, MMpad);
-    HM *hm = reinterpret_cast<HM *>(s.site + 4 * MMpad);      // [trial][lane]: the lane's hit mask for the trial's proposal
+    unsigned *hbrow = reinterpret_cast<unsigned *>(s.site + 4 * MMpad);   // [trial]: which lanes hold hits for the trial's proposal
+    HM *hm = reinterpret_cast<HM *>(hbrow + 32);               // [trial][lane]: the lane's hit mask for the trial's proposal
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, d.step_scale);
     const double *W = d.W + (size_t)cp.wall * 2 * MM;
@@ -181,35 +182,39 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     st_x = (float)(p_qx * b.invL); st_y = (float)(p_qy * b.invL); st_z = (float)(p_qz * b.invL);
                 }
                 s.stage[lane] = st_x; s.stage[32 + lane] = st_y; s.stage[64 + lane] = st_z;
+                hbrow[lane] = 0u;
                 const bool lite = __reduce_add_sync(FULL, (unsigned)nb0) > 2u * (unsigned)(te - tb);   // dense segment: no speculation
                 __syncwarp();
 
-                unsigned my_hb = 0, my_po = 0, my_pp = 0;
+                // per-lane interaction masks of MY trial with the other trials m of the segment:
+                //   my_in  bit m: proposal m lands in range of my particle's position      (m accepted -> my caches change)
+                //   my_po  bit m: particle m's position is in range of my proposal        (m accepted -> my partner set changes)
+                //   my_pp  bit m: proposal m is in range of my proposal                   (m accepted -> my partner set changes)
+                unsigned my_hb = 0, my_in = 0, my_po = 0, my_pp = 0;
                 if (!lite) {
                     // ================= phase 2: the segment's proposals against all slots, and against each other ==========
+                    // no votes in this loop: a lane records what concerns ITS particle / proposal (the relations are symmetric),
+                    // and the rare hit masks go to the 32x32 table with an atomicOr on the trial's row word
                     const float MGs = 12582912.f;
                     for (int t2 = tb & ~1; t2 < te; t2 += 2) {
-                        const float2 sx2 = *reinterpret_cast<const float2 *>(s.stage + t2);
-                        const float2 sy2 = *reinterpret_cast<const float2 *>(s.stage + 32 + t2);
-                        const float2 sz2 = *reinterpret_cast<const float2 *>(s.stage + 64 + t2);
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const int t = t2 + h;
-                            const float ax = h ? sx2.y : sx2.x, ay = h ? sy2.y : sy2.x, az = h ? sz2.y : sz2.x;
+                            const float ax = s.stage[t], ay = s.stage[32 + t], az = s.stage[64 + t];
                             const unsigned m = screen_slots<K, PZ>(sc, ax, ay, az, q) & validmask & ~((lane == t) ? 1u : 0u);
-                            const unsigned hb = __ballot_sync(FULL, m != 0);
-                            const unsigned po = __ballot_sync(FULL, (m & 1u) != 0);
-                            if (m) hm[t * 32 + lane] = (HM)m;
+                            if (m) { hm[t * 32 + lane] = (HM)m; atomicOr(hbrow + t, 1u << lane); }
+                            my_in |= (m & 1u) << t;
                             float dx = ax - st_x, dy = ay - st_y, dz = az - st_z;
                             dx -= (dx + MGs) - MGs;
                             dy -= (dy + MGs) - MGs;
                             if (PZ) dz = fmaf((dz * sc.inv_zper + MGs) - MGs, -sc.zper, dz);
                             const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            const unsigned pp = __ballot_sync(FULL, (r2 < sc.rc2s) && lane != t);
-                            if (lane == t) { my_hb = hb; my_po = po; my_pp = pp; }
+                            my_pp |= ((r2 < sc.rc2s) ? 1u : 0u) << t;
                         }
                     }
+                    my_pp &= ~(1u << lane);
                     __syncwarp();
+                    my_hb = hbrow[lane];
                     // ================= phase 3: lane t evaluates and decides its own trial =================
                     if (mine && !p_bad) {
                         unsigned hb = my_hb;
@@ -217,6 +222,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                             const int l = __ffs(hb) - 1;
                             hb &= hb - 1;
                             unsigned m = hm[lane * 32 + l];
+                            my_po |= (m & 1u) << l;
                             while (m) {
                                 const int k = __ffs(m) - 1;
                                 m &= m - 1;
@@ -268,15 +274,44 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     }
                     return touched;
                 };
+                // A "lonely" trial found nobody at its proposal and its particle has no partners now: committing it touches
+                // nobody else's caches.  Each pass of the loop is an EPOCH: f = the first pending trial that needs serial
+                // work (void or possibly void speculation, or an accepted trial with partners); the accepted lonely trials
+                // before f are committed together by their owner lanes, then f is handled alone.
+                const bool lonely = mine && !p_bad && pj < 0 && nb0 == 0;
+                const unsigned lowmask = (1u << lane) - 1u;
                 int cur = tb;
                 while (cur < te) {
                     const bool pending = mine && lane >= cur;
-                    const bool conf = pending && (lite || p_bad || ((dirty >> lane) & 1u) || (((my_pp | my_po) & A) != 0u));
-                    const unsigned confb = __ballot_sync(FULL, conf);
-                    const unsigned cand = confb | __ballot_sync(FULL, pending && p_acc);
-                    if (cand == 0u) break;
-                    const int t = __ffs(cand) - 1;
+                    const unsigned X = my_in | my_po | my_pp;
+                    const bool isdirty = (dirty >> lane) & 1u;
+                    // trials whose particle may still move in this segment (decision open, or accepted)
+                    const unsigned move = __ballot_sync(FULL, pending && (lite || p_bad || isdirty || p_acc));
+                    if (move == 0u) {                    // the rest are rejections; void only if an ACCEPTED trial interferes
+                        if (__ballot_sync(FULL, pending && (X & A) != 0u) == 0u) break;
+                    }
+                    const bool hard = pending && (lite || p_bad || isdirty || (X & (A | (move & lowmask))) != 0u || (p_acc && !lonely));
+                    const unsigned hardb = __ballot_sync(FULL, hard);
+                    const int f = hardb ? __ffs(hardb) - 1 : 32;
+                    const bool commit = pending && lane < f && p_acc;      // lonely, and nothing before it in the segment interferes
+                    const unsigned cm = __ballot_sync(FULL, commit);
+                    if (cm) {
+                        if (commit) {
+                            s.x[nl] = p_qx; s.y[nl] = p_qy; s.z[nl] = p_qz;
+                            s.ce[nl] = 4.0 * p_ew; s.cfx[nl] = 0.0; s.cfy[nl] = 0.0; s.cfz[nl] = p_fz;
+                            q.set(0, st_x, st_y, st_z);
+                            dE += p_dU;                 // SMC.c:341, summed per lane, reduced at the end of the sweep
+                        }
+                        A |= cm;
+                        nacc += __popc(cm);
+                        __syncwarp();
+                    }
+                    if (f >= te) break;
+                    const int t = f;
                     cur = t + 1;
+                    // with the epoch's commits known: does trial t's speculation stand?
+                    const unsigned confb = __ballot_sync(FULL, pending && (lite || p_bad || isdirty || (X & A) != 0u));
+                    if (!((confb >> t) & 1u) && !((__ballot_sync(FULL, p_acc) >> t) & 1u)) continue;    // a valid rejection
                     const int n = 32 * slot + t;
                     const unsigned okmask = validmask & ~((lane == t) ? 1u : 0u);
                     const int nbm = s.nb[n];

@@ -48,7 +48,7 @@ def droplet():
     return g[rs.permutation(N)].reshape(-1)
 
 
-variant = os.environ.get("SMCB_SWEEP_KERNEL", "coop")
+variant = os.environ.get("SMCB_SWEEP_KERNEL", "auto")
 for state in args.states.split(","):
     A = 0.02 if state == "droplet" else T
     with smcb.Engine(C, N, 3) as eng:
