@@ -70,47 +70,105 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (thermalised gas, all-particle kernel, droplet)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="batched/bulk workloads: weak = --chains (8192) chains PER GPU; strong = that many chains IN TOTAL, "
+                         "sharded over the GPUs (north_star: 1->8 GPUs on 8192 chains x N=256)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def _ref_worker(args):
-    """one host core = one independent chain of the compiled reference (oracle/_ref)"""
-    libname, nsweeps, seed = args
-    from oracle_bindings import GOLDEN_W_M3, RefLib
-    ref = RefLib(N_PART, M_SITES, fast=libname.endswith("_fast"))
-    R = ref.initializeBox(L_BOX, LZ_BOX)
-    W = GOLDEN_W_M3.copy()
-    ref.lib.oracle_srand(seed)
-    Rn = np.zeros_like(R)
-    j = ctypes.c_int(0)
-    e = ctypes.c_double(0.0)
-    t0 = time.perf_counter()
-    for _ in range(nsweeps):
-        ref.lib.oneParticleMoves(R, Rn, W, L_BOX, LZ_BOX, TEMP, TEMP, ctypes.byref(j), ctypes.byref(e))
-    return time.perf_counter() - t0, j.value
+# One PERSISTENT worker process per host core, each owning one independent chain of the compiled reference
+# (oracle/_ref) - the only parallel mode the reference has.  The library is loaded and the start lattice built
+# once, outside every timed window; a step is "every worker runs nsweeps sweeps", timed INSIDE the worker around
+# the oneParticleMoves loop (SMC.c:278-351); the step's time is the slowest worker's.
+def _ref_worker_main(conn, core, fast, seed):
+    try:
+        try:
+            os.sched_setaffinity(0, {core})
+        except (AttributeError, OSError):
+            pass
+        from oracle_bindings import GOLDEN_W_M3, RefLib
+        ref = RefLib(N_PART, M_SITES, fast=fast)
+        R = ref.initializeBox(L_BOX, LZ_BOX)
+        W = GOLDEN_W_M3.copy()
+        ref.lib.oracle_srand(seed)
+        Rn = np.zeros_like(R)
+        j = ctypes.c_int(0)
+        e = ctypes.c_double(0.0)
+        conn.send("ready")
+        while True:
+            nsweeps = conn.recv()
+            if nsweeps is None:
+                break
+            t0 = time.perf_counter()
+            for _ in range(nsweeps):
+                ref.lib.oneParticleMoves(R, Rn, W, L_BOX, LZ_BOX, TEMP, TEMP, ctypes.byref(j), ctypes.byref(e))
+            conn.send((time.perf_counter() - t0, j.value))
+    except Exception as ex:                       # surfaces in the parent instead of a silent hang
+        conn.send(("error", repr(ex)))
 
 
 def host_cores():
     try:
-        return len(os.sched_getaffinity(0))
+        return sorted(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        return list(range(os.cpu_count() or 1))
 
 
-def run_reference_steps(pool, cores, nsweeps, nsteps, fast=False):
-    """nsteps x (every core runs nsweeps sweeps of its own chain); returns wall seconds per step"""
-    lib = "ref_fast" if fast else "ref"
-    times = []
-    for s in range(nsteps):
-        t0 = time.perf_counter()
-        pool.map(_ref_worker, [(lib, nsweeps, 1000 * s + c) for c in range(cores)])
-        times.append(time.perf_counter() - t0)
-    return times
+class RefWorkers:
+    def __init__(self, fast=False):
+        ctx = mp.get_context("fork")
+        self.cores = host_cores()
+        self.procs, self.conns = [], []
+        for i, core in enumerate(self.cores):
+            pc, cc = ctx.Pipe()
+            pr = ctx.Process(target=_ref_worker_main, args=(cc, core, fast, 1000 + i), daemon=True)
+            pr.start()
+            self.procs.append(pr); self.conns.append(pc)
+        for c in self.conns:
+            msg = c.recv()
+            if msg != "ready":
+                raise RuntimeError(f"reference worker failed: {msg}")
+
+    def step(self, nsweeps):
+        """every worker runs nsweeps sweeps; returns the slowest worker's in-loop seconds"""
+        for c in self.conns:
+            c.send(nsweeps)
+        out = [c.recv() for c in self.conns]
+        for o in out:
+            if o[0] == "error":
+                raise RuntimeError(f"reference worker failed: {o[1]}")
+        return max(o[0] for o in out)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(None)
+            except (BrokenPipeError, OSError):
+                pass
+        for pr in self.procs:
+            pr.join(timeout=5)
 
 
 def pairs_per_sweep(n):
     return 2.0 * n * (n - 1)
+
+
+def run_reference(nsteps, warmup, min_step_s=0.25, fast=False):
+    """(value pair-interactions/s, cores, sweeps per step, total timed seconds): `warmup` untimed steps, then nsteps
+    timed ones of at least min_step_s each (a step of 40 sweeps is 80 ms of CPU work: too short to time from outside)"""
+    w = RefWorkers(fast)
+    try:
+        t40 = w.step(40)                                    # also the first warm-up step
+        nsweeps = int(max(40, np.ceil(40 * min_step_s / max(t40, 1e-4))))
+        for _ in range(max(0, warmup - 1)):
+            w.step(nsweeps)
+        total = sum(w.step(nsweeps) for _ in range(nsteps))
+    finally:
+        w.close()
+    cores = len(w.cores)
+    return cores * nsweeps * nsteps * pairs_per_sweep(N_PART) / total, cores, nsweeps, total
 
 
 def reference_arm(args):
@@ -121,24 +179,20 @@ def reference_arm(args):
     if not os.path.exists(ref_so):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)"}))
         return
-    cores = host_cores()
-    nsweeps = max(1, min(args.sweeps_per_step, 40))
-    with mp.get_context("fork").Pool(cores) as pool:
-        run_reference_steps(pool, cores, 2, max(1, min(args.warmup, 3)))
-        times = run_reference_steps(pool, cores, nsweeps, args.steps)
-    total = sum(times)
-    sweeps = cores * nsweeps * args.steps
-    value = sweeps * pairs_per_sweep(N_PART) / total
+    nsteps = max(1, min(args.steps, 40))
+    value, cores, nsweeps, total = run_reference(nsteps, max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": "pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
-        "chain_steps_per_s": sweeps / total, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "chain_steps_per_s": value / pairs_per_sweep(N_PART), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"reference oneParticleMoves (SMC.c:278-351), N={N_PART} wall, one chain per host core",
-                   "N": N_PART, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": TEMP,
-                   "sweeps_per_step": nsweeps, "chains": cores},
+        "config": {"workload": f"reference oneParticleMoves (SMC.c:278-351), N={N_PART} with wall (BASELINE configs[2] chains), "
+                               "one chain per host core", "N": N_PART, "M": M_SITES, "L": L_BOX, "Lz": LZ_BOX, "T": TEMP, "A": TEMP,
+                   "sweeps_per_step": nsweeps, "chains": cores, "start": "initializeBox fcc lattice",
+                   "timing": "inside each persistent worker around its sweep loop; a step lasts as long as its slowest worker"},
         "cpu_baseline": {"value": value, "unit": "pair-interactions/s", "cores": cores, "kind": "reference",
-                         "sample": f"{cores} chains x {nsweeps} sweeps x {args.steps} steps, gcc -O2 -ffp-contract=off build of /root/reference"},
+                         "sample": f"{cores} chains x {nsweeps} sweeps x {nsteps} steps ({total:.1f} s timed), "
+                                   "gcc -O2 -ffp-contract=off build of /root/reference"},
         "e2e": {"value": value, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -146,25 +200,20 @@ def reference_arm(args):
 
 
 def cpu_baseline(args):
-    """bounded sample of the reference on all host cores (rank 0, N=1 only)"""
+    """bounded sample of the reference on all host cores (rank 0, N=1 only): the same measurement as --impl reference"""
     ref_so = os.path.join(ROOT, "oracle", "_ref", f"libref_N{N_PART}_M{M_SITES}.so")
     if not os.path.exists(ref_so):
         return None
-    cores = host_cores()
-    out = {}
-    with mp.get_context("fork").Pool(cores) as pool:
-        for fast in (False, True):
-            run_reference_steps(pool, cores, 2, 1, fast)
-            t_probe = run_reference_steps(pool, cores, 10, 1, fast)[0]
-            nsweeps = int(max(10, min(4000, 10 * (args.cpu_seconds / 2) / max(t_probe, 1e-3))))
-            t = run_reference_steps(pool, cores, nsweeps, 1, fast)[0]
-            out["fast" if fast else "parity"] = (cores * nsweeps / t, nsweeps, t)
-    sps, nsw, t = out["parity"]
-    return {"value": sps * pairs_per_sweep(N_PART), "unit": "pair-interactions/s", "cores": cores, "kind": "reference",
-            "chain_steps_per_s": sps, "chain_steps_per_s_per_core": sps / cores,
-            "sample": f"{cores} host cores x 1 chain x {nsw} sweeps of oneParticleMoves (N={N_PART}, wall), {t:.1f} s, "
-                      "reference compiled -O2 -ffp-contract=off",
-            "courtesy_O3_avx2_value": out["fast"][0] * pairs_per_sweep(N_PART)}
+    nsteps = max(4, int(args.cpu_seconds / 2 / 0.5))
+    value, cores, nsweeps, total = run_reference(nsteps, 2, min_step_s=0.5)
+    out = {"value": value, "unit": "pair-interactions/s", "cores": cores, "kind": "reference",
+           "chain_steps_per_s": value / pairs_per_sweep(N_PART), "chain_steps_per_s_per_core": value / pairs_per_sweep(N_PART) / cores,
+           "sample": f"{cores} host cores x 1 chain x {nsweeps} sweeps x {nsteps} steps of oneParticleMoves (N={N_PART}, wall), "
+                     f"{total:.1f} s timed inside the workers, reference compiled -O2 -ffp-contract=off"}
+    if os.path.exists(ref_so.replace(".so", "_fast.so")):
+        vfast, _, _, _ = run_reference(max(2, nsteps // 2), 1, min_step_s=0.5, fast=True)
+        out["courtesy_O3_avx2_value"] = vfast
+    return out
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -178,7 +227,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -240,6 +289,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     Cn, N, S = args.chains or 8192, N_PART, args.sweeps_per_step
+    strong_batched = args.scaling == "strong" and args.workload in ("batched", "bulk")
+    total_batched = float(Cn) if strong_batched else float(Cn) * world
+    if strong_batched:
+        shard_b = smcb.shard_chains(int(total_batched), world, rank)
+        Cn = shard_b.nchains
     total_largeN = 256
     if args.workload == "largeN":                   # configs[4]: 256 chains x N=4096 in total, strong-sharded
         N, args.kernel = 4096, ("sweep" if args.largeN_sweep else "allparticle")
@@ -277,16 +331,19 @@ def main():
         X[:, :2] -= L_BOX * np.rint(X[:, :2] / L_BOX)
         X[:, 2] -= Pz * np.rint(X[:, 2] / Pz)
     R0 = X.reshape(-1)
-    if args.start == "droplet":
-        nzl = 4 if N <= 512 else 8
-        nxy = int(np.ceil(np.sqrt(N / nzl)))
-        g = np.array([(i, j, k) for k in range(nzl) for i in range(nxy) for j in range(nxy)], dtype=float)[:N]
-        g[:, 0] = (g[:, 0] - nxy / 2) * 1.12
-        g[:, 1] = (g[:, 1] - nxy / 2) * 1.12
+    def droplet_start(n):
+        nzl = 4 if n <= 512 else 8
+        nx = int(np.ceil(np.sqrt(n / nzl)))
+        g = np.array([(i, j, k) for k in range(nzl) for i in range(nx) for j in range(nx)], dtype=float)[:n]
+        g[:, 0] = (g[:, 0] - nx / 2) * 1.12
+        g[:, 1] = (g[:, 1] - nx / 2) * 1.12
         g[:, 2] = -LZ_BOX / 2 + 0.95 + g[:, 2] * 1.12
         rs = np.random.default_rng(7)
         g += (rs.random(g.shape) * 2 - 1) * 0.05
-        R0 = g[rs.permutation(N)].reshape(-1)
+        return g[rs.permutation(n)].reshape(-1)
+
+    if args.start == "droplet":
+        R0 = droplet_start(N)
 
     eng = smcb.Engine(Cn, N, M_SITES, device=local)
     if grid:
@@ -298,18 +355,22 @@ def main():
     elif bulk:
         A = 0.01 if args.kernel == "sweep" else 1e-4      # a liquid: the prototype's own A is 4e-8 (SMC_noMPI_noWall.c:192)
         eng.set_params(smcb.default_params(L=Lb, Lz=Lb, T=1.0, A=A, rc2=Lb * Lb / 4, flags=smcb.PERIODIC_Z), None, ngroups=1)
-        chain0 = rank * Cn
+        chain0 = shard_b.chain0 if strong_batched else rank * Cn
     else:
         eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=A), GOLDEN_W_M3, ngroups=1)
-        chain0 = rank * Cn
+        chain0 = shard_b.chain0 if strong_batched else rank * Cn
     eng.obs_configure(nebins=64, e_lo=-8.0, e_hi=2.0)
     eng.broadcast_positions(R0)
     eng.set_rng(12345, chain0, 0)
     info = eng.device_info()
     lay = eng.obs_layout()
 
+    # the reduce is done on DELTAS: every step the rank's block (what it gathered since the last reset) is exported,
+    # summed over ranks, added to the running job totals below, and reset (Rbin survives the reset)
     obs_cnt = torch.zeros(lay.u64_total, dtype=torch.int64, device="cuda")
     obs_mom = torch.zeros(lay.f64_total, dtype=torch.float64, device="cuda")
+    tot_cnt = torch.zeros(lay.u64_total, dtype=torch.int64, device="cuda")
+    tot_mom = torch.zeros(lay.f64_total, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     def run_kernel(kernel):
@@ -327,14 +388,15 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         smcb.allreduce_observables(obs_cnt, obs_mom)
+        tot_cnt.add_(obs_cnt); tot_mom.add_(obs_mom)
         e1.record()
         torch.cuda.synchronize()
-        eng.obs_reset()          # ranks keep accumulating deltas; the reduced block lives in obs_cnt/obs_mom
+        eng.obs_reset()          # accumulators only: the next delta starts from zero, mobility keeps its Rbin
         return e0.elapsed_time(e1)
 
     def one_step(kernel):
         k_ms = run_kernel(kernel)
-        pairs = eng.last_pair_counts()
+        pairs = eng.last_pair_counts() + (eng.last_pair_tests(),)
         eng.gather()
         g_ms = eng.last_kernel_ms()[0]
         c_ms = allreduce_obs()
@@ -346,7 +408,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_leg(kernel, nsteps, warmup, sample_clocks=False):
+    def timed_leg(kernel, nsteps, warmup, sample_clocks=False, want_msd=True):
         """`warmup` untimed steps, then exactly `nsteps` steps between barriers; device times (CUDA events
         on the engine's stream) summed per rank, max over ranks"""
         for _ in range(warmup):
@@ -357,14 +419,15 @@ def main():
             sampler.start()
         t0 = time.perf_counter()
         k_tot = g_tot = c_tot = 0.0
-        pairs_tot = pairs_cut = 0
+        pairs_tot = pairs_cut = pairs_exec = 0
         eng.reset_counters()
+        R_before = eng.get_positions() if want_msd else None
         for _ in range(nsteps):
             flush.fill_(1)                      # L2 flush between timed iterations (untimed)
             torch.cuda.synchronize()
             k_ms, g_ms, c_ms, pairs = one_step(kernel)
             k_tot += k_ms; g_tot += g_ms; c_tot += c_ms
-            pairs_tot += pairs[0]; pairs_cut += pairs[1]
+            pairs_tot += pairs[0]; pairs_cut += pairs[1]; pairs_exec += pairs[2]
         barrier()
         wall = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None
@@ -372,14 +435,26 @@ def main():
         dev_ms = smcb.max_over_ranks(k_tot + g_tot + c_tot, device="cuda")
         k_max = smcb.max_over_ranks(k_tot, device="cuda")
         unit_pairs = pairs_per_sweep(N) if kernel == "sweep" else float(N) * (N - 1)
-        total_chains = float(world) * Cn if args.workload in ("batched", "bulk") else (float(grid[4]) if grid else total_largeN)
+        total_chains = total_batched if args.workload in ("batched", "bulk") else (float(grid[4]) if grid else total_largeN)
         chain_steps = total_chains * S * nsteps
         flops = FLOPS_PAIR * pairs_tot + FLOPS_INCUT * pairs_cut
+        flops_exec = FLOPS_PAIR * pairs_exec + FLOPS_INCUT * pairs_cut
+        msd = None
+        if want_msd:
+            # sampling efficiency: mean squared displacement of a molecule over the leg (minimum image in x,y; in z too
+            # for the bulk geometry), per second of device time - what an accepted step is worth, for comparing kernels
+            dR = (eng.get_positions() - R_before).reshape(Cn, N, 3)
+            per = np.array([Lb, Lb, Lb]) if bulk else np.array([L_BOX, L_BOX, np.inf])
+            dR -= np.where(np.isfinite(per), per, 1.0) * np.rint(dR / per)
+            msd = float(np.mean(np.sum(dR * dR, axis=2)))
         return {"value": chain_steps * unit_pairs / (dev_ms * 1e-3), "chain_steps_per_s": chain_steps / (dev_ms * 1e-3),
                 "ms_per_step": dev_ms / nsteps, "kernel_ms_per_step": k_max / nsteps, "gather_ms_per_step": g_tot / nsteps,
                 "allreduce_ms_per_step": c_tot / nsteps, "wall_s": wall, "clocks": clocks,
                 "pairs_in_cutoff_frac": pairs_cut / max(1, pairs_tot), "acceptance": float(na.sum()) / max(1, int(nt.sum())),
-                "achieved_tflops": flops / (k_tot * 1e-3) / 1e12, "unit_pairs": unit_pairs}
+                "achieved_tflops": flops / (k_tot * 1e-3) / 1e12, "executed_tflops": flops_exec / (k_tot * 1e-3) / 1e12,
+                "pairs_nominal": pairs_tot, "pairs_executed": pairs_exec, "pairs_in_cutoff": pairs_cut, "unit_pairs": unit_pairs,
+                "msd_per_leg": msd, "msd_per_s": (msd / (dev_ms * 1e-3)) if msd is not None else None,
+                "msd_per_chain_step": (msd / (S * nsteps)) if msd is not None else None}
 
     fp64_peak, _ = eng.measure_fp64_peak()
     W = max(args.warmup, 3)
@@ -391,13 +466,16 @@ def main():
         host_R = torch.empty((Cn, 3 * N), dtype=torch.float64).pin_memory().numpy()
         nsteps_e2e = max(3, min(args.steps, 20))            # the same window of the trajectory as the device-resident leg
 
+        host_E = torch.empty(Cn, dtype=torch.float64).pin_memory().numpy()
+        host_na = torch.empty(Cn, dtype=torch.int64).pin_memory().numpy()
+        host_nt = torch.empty(Cn, dtype=torch.int64).pin_memory().numpy()
+
         def e2e_step():
-            eng.set_positions(host_R)                  # H2D of the step's inputs
-            run_kernel(args.kernel)
-            eng.gather()
+            # ONE C-ABI call with host buffers: H2D of the step's positions, energy refresh, S sweeps, gather, D2H of the new
+            # positions and the chain state; inside, four chain blocks on four streams overlap their copies and kernels
+            eng.sweep_host(host_R, S, mode, kernel=args.kernel, gather=True, E=host_E, naccept=host_na, ntrials=host_nt)
             allreduce_obs()
-            eng.get_positions(host_R)                  # D2H of the step's results
-            return eng.chain_state()
+            return host_E
 
         # same start as the device-resident leg: the lattice, the same streams, W warm-up steps
         eng.broadcast_positions(R0)
@@ -411,37 +489,61 @@ def main():
             e2e_step()
         barrier()
         te = smcb.max_over_ranks(time.perf_counter() - t0, device="cuda")
-        total_chains = float(world) * Cn if args.workload in ("batched", "bulk") else (float(grid[4]) if grid else total_largeN)
+        total_chains = total_batched if args.workload in ("batched", "bulk") else (float(grid[4]) if grid else total_largeN)
         e2e = {"value": total_chains * S * nsteps_e2e * main["unit_pairs"] / te, "unit": "pair-interactions/s",
                "chain_steps_per_s": total_chains * S * nsteps_e2e / te, "steps": nsteps_e2e,
                "h2d_bytes_per_step": int(Cn * 3 * N * 8), "d2h_bytes_per_step": int(Cn * 3 * N * 8 + Cn * 24),
-               "timing": "host wall clock around set_positions -> kernel -> gather -> get_positions -> chain_state; same start "
+               "timing": "host wall clock around smcb_sweep_host (pinned host positions up, energy refresh, sweeps, gather, positions + "
+                         "chain state down; four chain blocks pipelined on four streams) + the observable all-reduce; same start "
                          "(lattice + warm-up steps) as the device-resident leg, no L2 flush between steps"}
 
     # ---- extra legs (reported beside the headline, same JSON line) -----------------------------
+    LEG_KEYS = ("value", "chain_steps_per_s", "ms_per_step", "kernel_ms_per_step", "pairs_in_cutoff_frac", "acceptance",
+                "msd_per_chain_step", "msd_per_s")
     extra = {}
-    if args.workload == "batched" and args.kernel == "sweep" and mode == smcb.FAST and args.start == "lattice":
+    if args.workload == "batched" and args.kernel == "sweep" and mode == smcb.FAST and args.start == "lattice" and not args.no_extra:
+        short = max(2, min(args.steps, 3))
+
+        def leg(kernel, nsteps, warmup, **more):
+            r = timed_leg(kernel, nsteps, warmup)
+            out = {k: r[k] for k in LEG_KEYS}
+            out.update(roofline_frac_nominal=r["achieved_tflops"] / fp64_peak, roofline_frac_executed=r["executed_tflops"] / fp64_peak, **more)
+            return out
+
         if args.thermalise > 0:
             # sMC's thermalisation (2A, SMC.c:110-125) so molecules reach the wall and partners become common
             eng.set_step_scale(2.0)
             eng.sweep(args.thermalise, mode)
             eng.set_step_scale(1.0)
-            th = timed_leg("sweep", max(2, min(args.steps, 3)), 1)
-            extra["thermalised"] = {k: th[k] for k in ("value", "chain_steps_per_s", "ms_per_step", "kernel_ms_per_step",
-                                                       "pairs_in_cutoff_frac", "acceptance")}
-            extra["thermalised"].update(sweeps_before=args.thermalise, roofline_frac=th["achieved_tflops"] / fp64_peak)
-        # north-star kernel B on the same chains: all-particle steps need a small A to be accepted at all
+            extra["thermalised"] = leg("sweep", short, 1, sweeps_before=args.thermalise)
+        # north-star kernel B on the same chains: all-particle steps need a small A to be accepted at all; the step size is
+        # set per chain by smcb_tune_step_size (target acceptance 0.5) and the sampling efficiency reported as MSD
         eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=2e-4), GOLDEN_W_M3, ngroups=1)
         eng.obs_configure(nebins=64, e_lo=-8.0, e_hi=2.0)
         eng.broadcast_positions(R0)
-        ap_ = timed_leg("allparticle", max(2, min(args.steps, 3)), 2)
-        extra["allparticle_kernel"] = {k: ap_[k] for k in ("value", "chain_steps_per_s", "ms_per_step", "kernel_ms_per_step",
-                                                            "pairs_in_cutoff_frac", "acceptance")}
-        extra["allparticle_kernel"].update(A=2e-4, roofline_frac=ap_["achieved_tflops"] / fp64_peak,
-                                           note="one all-particle Smart-MC step = N(N-1) ordered pair-interactions")
+        A_ap = eng.tune_step_size("allparticle", mode, target=0.5, rounds=8, nsteps_per_round=20)
+        extra["allparticle_kernel"] = leg("allparticle", short, 2, A_median=float(np.median(A_ap)), A_tuned_for_acceptance=0.5,
+                                          note="one all-particle Smart-MC step = N(N-1) ordered pair-interactions; msd_* = mean squared "
+                                               "displacement of a molecule per step / per second of device time (sampling efficiency)")
+        # the condensed phase (all molecules in a droplet on the wall, the state long reference runs end in): both kernels,
+        # step sizes tuned to acceptance 0.5 (sweep) / 0.3 (all-particle)
+        Rd = droplet_start(N)
+        for kname, target in (("sweep", 0.5), ("allparticle", 0.3)):
+            eng.set_params(smcb.default_params(L=L_BOX, Lz=LZ_BOX, T=TEMP, A=0.02 if kname == "sweep" else 1e-5), GOLDEN_W_M3, ngroups=1)
+            eng.obs_configure(nebins=64, e_lo=-8.0, e_hi=2.0)
+            eng.broadcast_positions(Rd)
+            eng.set_rng(12345, chain0, 0)
+            if kname == "sweep":
+                eng.sweep(100, mode)                 # let the compressed start block relax before tuning
+            A_d = eng.tune_step_size(kname, mode, target=target, rounds=8, nsteps_per_round=10 if kname == "sweep" else 40)
+            extra[f"droplet_{kname}"] = leg(kname, 2, 1, A_median=float(np.median(A_d)), A_tuned_for_acceptance=target)
 
     if rank == 0:
         traffic, traffic_note = None, None
+        ncu = {}
+        npath = os.path.join(ROOT, "profiles", "roofline_ncu.json")
+        if os.path.exists(npath):
+            ncu = json.load(open(npath)).get(f"{args.kernel}:{args.start}", {})
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath)).get(args.kernel)
@@ -453,7 +555,8 @@ def main():
             "chain_steps_per_s": main["chain_steps_per_s"],
             "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": main["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak" if args.workload in ("batched", "bulk") or (grid and args.chains) else "strong", "vs_baseline": None,
+            "scaling": ("strong" if strong_batched else "weak") if args.workload in ("batched", "bulk") else ("weak" if (grid and args.chains) else "strong"),
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": (f"{Cn} chains/GPU x N={N} with wall (BASELINE configs[2])" if args.workload == "batched"
                                     else f"{Cn} chains/GPU x N={N} bulk, 3-D periodic, rho*=0.5, T*=1.0 (BASELINE configs[0] geometry)" if bulk
@@ -470,13 +573,21 @@ def main():
             "allreduce_ms_per_step": main["allreduce_ms_per_step"], "wall_s_timed_region": main["wall_s"],
             "pairs_in_cutoff_frac": main["pairs_in_cutoff_frac"], "acceptance": main["acceptance"],
             "roofline": {"bound": "fp64", "achieved": main["achieved_tflops"], "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": main["achieved_tflops"] / fp64_peak, "traffic": traffic, "traffic_note": traffic_note,
-                         "note": "ALGORITHMIC flops = 17 per ordered pair-interaction + 16 more inside the cutoff (SURVEY §8d), "
-                                 "a sweep counted as the reference executes it: 2N(N-1) pair-interactions (old + proposed "
-                                 "position of every trial).  The kernel evaluates fewer: old-position terms are cached, and the "
-                                 "cutoff screen runs in packed FP32 (exact FP64 for the pairs inside), so frac is a figure of "
-                                 "merit against the FP64 peak, not FP64-pipe utilisation - that is in profiles/ (ncu).  peak = "
-                                 "DFMA peak measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"},
+                         "frac": main["achieved_tflops"] / fp64_peak, "frac_nominal": main["achieved_tflops"] / fp64_peak,
+                         "frac_executed": main["executed_tflops"] / fp64_peak,
+                         "pairs_nominal_per_step": main["pairs_nominal"] / args.steps, "pairs_executed_per_step": main["pairs_executed"] / args.steps,
+                         "pairs_in_cutoff_per_step": main["pairs_in_cutoff"] / args.steps,
+                         "fp64_pipe_pct": ncu.get("fp64_pipe_pct"), "issue_pct": ncu.get("issue_pct"), "ncu_source": ncu.get("source"),
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "note": "frac = frac_nominal: ALGORITHMIC flops (17 per ordered pair-interaction + 16 more inside the cutoff, "
+                                 "SURVEY §8d) of a sweep counted as the reference executes it - 2N(N-1) pair-interactions, old + proposed "
+                                 "position of every trial - over the measured DFMA peak.  It is a figure of merit, not a utilisation: the "
+                                 "kernels execute fewer pair tests (pairs_executed: old-position terms are cached; the all-particle kernel "
+                                 "visits every unordered pair once) and run the cutoff test in packed FP32.  frac_executed counts only the "
+                                 "pair tests actually executed (17 flops each, FP32) plus 16 FP64 flops per pair inside the cutoff; "
+                                 "fp64_pipe_pct / issue_pct are the ncu pipe and issue-slot utilisations of the same kernel on this "
+                                 "workload (profiles/, per round).  peak = DFMA peak measured live on this GPU (MEASURED_PEAKS.json has no "
+                                 "FP64 entry)"},
             "clocks": main["clocks"], "gpu_launches": args.steps * 4, "device": info,
         }
         line.update(extra)

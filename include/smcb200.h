@@ -17,7 +17,7 @@
  *   - every call returns 0 on success, <0 on error (smcb_last_error() has the
  *     text).  There is NO CPU fallback: without a CUDA device smcb_create fails.
  *   - calls on one handle are serialised by the caller; different handles are
- *     independent.  All calls are synchronous on return.
+ *     independent.  All calls are synchronous on return (smcb_sweep_host overlaps copies and kernels internally).
  *   - no identifier below collides with the reference's macros (N, M, a0, b0, rank, Ncx, Ncz,
  *     KMAX ...: SMC.h:26-61), so a translation unit built on SMC.h can include this header.
  */
@@ -146,6 +146,19 @@ int smcb_sweep_traced(smcb_engine *e, int nsweeps, int mode,
 /* thermalisation helper: sweeps run with A*scale (sMC uses 2, SMC.c:110) */
 int smcb_set_step_scale(smcb_engine *e, double scale);
 
+/* ---- the host-buffer step, pipelined --------------------------------------
+ * What a caller that keeps its configurations in HOST memory does per step - the reference's sMC owns R in host
+ * memory and calls oneParticleMoves(R, ...) in place (SMC.c:117,195) - as ONE call: upload R (nchains*3N, AoS),
+ * E <- energy + wallsEnergy (SMC.c:48), nsteps sweeps (kernel = 0, oneParticleMoves) or all-particle steps
+ * (kernel = 1) from the engine's Philox stream, optionally one gather of the observables (SMC.c:137-141), download
+ * the new positions into R and the chain state into E / naccept / ntrials (each nullable, nchains entries).
+ * The batch is processed as four blocks of chains on four streams so one block's PCIe copies overlap the other
+ * blocks' kernels; pass page-locked buffers (cudaHostAlloc / torch pin_memory) to get the overlap.  Results are
+ * identical to smcb_set_positions + smcb_sweep (smcb_step_allparticle) + smcb_gather + smcb_get_positions +
+ * smcb_get_chain_state. */
+int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, int kernel, int gather,
+                    double *E, int64_t *naccept, int64_t *ntrials);
+
 /* ---- the all-particle Smart-MC step (north-star kernel B) ----------------
  * Every particle of a chain is displaced at once, d_i = F_i A/T + xi_i, forces
  * and energy are recomputed at the proposal with a tiled O(N^2) pair kernel
@@ -156,6 +169,17 @@ int smcb_set_step_scale(smcb_engine *e, double scale);
 int smcb_step_allparticle_fed(smcb_engine *e, int nsteps, int mode,
                               const double *xi, const double *u, double *lnap, uint8_t *accepted);
 int smcb_step_allparticle(smcb_engine *e, int nsteps, int mode);
+
+/* ---- step-size control (before production) -------------------------------
+ * The reference fixes A = gamma*T for every state (main.c:48-51); a whole-configuration move (kernel = 1) with that A
+ * is never accepted, and in a condensed phase the single-particle sweep's acceptance collapses too.  This runs `rounds`
+ * short batches of nsteps_per_round sweeps (kernel = 0) or all-particle steps (kernel = 1) and after each multiplies
+ * every chain's A by exp(gain * (its acceptance - target)) with a decreasing gain, so that A settles where the
+ * acceptance is `target`.  The chains move while it runs (it is part of the thermalisation; adapting A during
+ * production would break detailed balance).  Chains sharing one parameter set get their own copy.  Accept/trial
+ * counters are cleared on return. */
+int smcb_tune_step_size(smcb_engine *e, int kernel, int mode, double target, int rounds, int nsteps_per_round);
+int smcb_get_step_sizes(smcb_engine *e, double *A);            /* nchains doubles */
 
 /* ---- chain state -------------------------------------------------------- */
 /* E: running total potential energy (set by smcb_refresh_energy or any step);
@@ -192,6 +216,9 @@ typedef struct smcb_obs_layout {
 int smcb_obs_configure(smcb_engine *e, int nebins, double e_lo, double e_hi);
 int smcb_obs_layout_get(smcb_engine *e, smcb_obs_layout *out);
 int smcb_gather(smcb_engine *e);
+/* zero the accumulators (counters and moments).  Rbin - where every particle was at the last gather (SMC.c:921-924) -
+ * is chain state and is KEPT, so a run that exports/reduces/resets after every gather counts the same mobility as
+ * one that never resets.  (smcb_set_params / smcb_obs_configure start from Rbin = 0, like sMC's calloc, SMC.c:54.) */
 int smcb_obs_reset(smcb_engine *e);
 int smcb_obs_get(smcb_engine *e, uint64_t *counters, double *moments);           /* host copies */
 /* device-side exchange for an NCCL all-reduce done by the host program: copy
@@ -204,8 +231,15 @@ int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void 
  * ends up holding the job's totals.  All engines must have the same observable layout.  NCCL is
  * loaded at run time (dlopen "libnccl.so.2"); SMCB_ERR_STATE if it is not available.  With one
  * process per GPU (torch.distributed, MPI) use smcb_obs_export_device / _import_device and the
- * launcher's own all-reduce instead. */
+ * launcher's own all-reduce instead.
+ * The sum is IN PLACE, so it is valid ONCE per accumulation window: after it every block holds the job's totals, and
+ * gathering more samples on top (or reducing again) would count the other engines' samples n times.  The engines
+ * remember it: smcb_gather and a second smcb_obs_allreduce return SMCB_ERR_STATE until smcb_obs_reset.  To reduce
+ * after EVERY gather, reduce deltas instead: export the block, all-reduce the copy, add it to your running total,
+ * smcb_obs_reset (bench.py does this through smcb_obs_export_device). */
 int smcb_obs_allreduce(smcb_engine **engines, int n);
+/* release the NCCL communicators smcb_obs_allreduce caches between calls (optional) */
+int smcb_obs_allreduce_teardown(void);
 /* per-chain Rbin (voxel of each particle at the last gather), nchains*N ints */
 int smcb_get_rbin(smcb_engine *e, int32_t *rbin);
 int smcb_set_rbin(smcb_engine *e, const int32_t *rbin);
@@ -227,6 +261,11 @@ int smcb_checkpoint_load(smcb_engine *e, const char *path);
 int smcb_last_kernel_ms(smcb_engine *e, float *ms, int *launches);
 /* pairs inside the cutoff counted by the last sweep/step call (roofline numerator) */
 int smcb_last_pair_counts(smcb_engine *e, uint64_t *pairs_total, uint64_t *pairs_in_cutoff);
+/* pair distance tests the kernels of the last sweep/step call actually EXECUTED.  pairs_total above counts a sweep as the
+ * reference executes it (2N(N-1) ordered pair-interactions: energySingle + forceSingle at the old and the proposed
+ * position, SMC.c:300-321); the FAST kernels cache the old-position terms and screen in packed FP32, the all-particle
+ * kernel visits every unordered pair once, so they execute fewer - this is the count behind roofline.frac_executed */
+int smcb_last_pair_tests(smcb_engine *e, uint64_t *pair_tests_executed);
 /* FP64 FMA peak of this device measured with a dependent-free DFMA kernel; TFLOP/s */
 int smcb_measure_fp64_peak(smcb_engine *e, double *tflops, float *ms);
 /* raw device pointers for the stream-resident benchmark path (positions SoA

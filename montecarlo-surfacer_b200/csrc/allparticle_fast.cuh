@@ -398,7 +398,11 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
             d.E[chain] = U;
             d.nacc[chain] += nacc;
             d.ntri[chain] += a.nsteps;
-            if (d.pair_counts) atomicAdd(d.pair_counts, (unsigned long long)a.nsteps * (unsigned long long)N * (N - 1));
+            if (d.pair_counts) {
+                atomicAdd(d.pair_counts, (unsigned long long)a.nsteps * (unsigned long long)N * (N - 1));
+                // screened pair tests: every ordered pair, or every unordered pair once in the half-shell variant
+                atomicAdd(d.pair_counts + 2, (unsigned long long)(a.nsteps + (a.refresh ? 1 : 0)) * (unsigned long long)N * (N - 1) / (HALF ? 2ull : 1ull));
+            }
         }
         if (d.pair_counts) atomicAdd(d.pair_counts + 1, (unsigned long long)c[0]);
     }

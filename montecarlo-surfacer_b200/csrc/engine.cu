@@ -7,9 +7,11 @@
 // kernels or returns an error.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -58,6 +60,15 @@ struct smcb_engine {
     int device = 0, C = 0, N = 0, Npad = 0, M = 0, nwalls = 0, ngroups = 1, nparams = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // smcb_sweep_host: the batch is cut into kParts chain blocks, each on its own stream, so that one block's
+    // PCIe copies overlap the other blocks' kernels
+    static constexpr int kParts = 4;
+    cudaStream_t pstream[kParts] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pev[kParts] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pstart = nullptr;
+    unsigned long long *pairs_pinned = nullptr;     // pinned landing area of the pair counters
+    uint64_t params_hash = 0;                       // FNV-1a of the chain parameters and wall tables (checkpoint guard)
+    bool obs_reduced = false;                       // the block holds an in-place all-reduced total: no further gathers until a reset
     DevBuf<smcb_chain_params> params;
     DevBuf<double> W, pos, E, stage, F, Fn, dl, e_lj, f_lj, e_wall, f_wall, totals, moments, peak_out;
     DevBuf<double> fed_a, fed_b;            // host-fed random inputs
@@ -80,7 +91,7 @@ struct smcb_engine {
     double e_lo = -8.0, e_hi = 2.0;
     float last_ms = 0.f;
     int last_launches = 0;
-    unsigned long long last_pairs[2] = {0, 0};
+    unsigned long long last_pairs[3] = {0, 0, 0};
     int sweep_dense = 0;                    // the last FAST sweep launch found > 2 % of the pairs inside the cutoff
 
     DevChains chains()
@@ -120,6 +131,7 @@ struct CkptHeader {
     uint64_t seed, step;
     double step_scale, e_lo, e_hi;
     uint64_t n_counters, n_moments;
+    uint64_t params_hash;          // version 2: FNV-1a of the chain parameters and wall tables the run was made with
 };
 
 template <typename T>
@@ -131,14 +143,6 @@ int put(FILE *f, const T *dev, size_t n, cudaStream_t st, std::vector<unsigned c
     return fwrite(buf.data(), 1, buf.size(), f) == buf.size() ? 0 : -2;
 }
 
-template <typename T>
-int get(FILE *f, T *dev, size_t n, cudaStream_t st, std::vector<unsigned char> &buf)
-{
-    buf.resize(n * sizeof(T));
-    if (fread(buf.data(), 1, buf.size(), f) != buf.size()) return -2;
-    if (cudaMemcpyAsync(dev, buf.data(), buf.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
-    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
-}
 }  // namespace
 
 extern "C" {
@@ -163,17 +167,23 @@ int smcb_create(smcb_engine **out, int device, int nchains, int N, int M)
     cudaError_t a = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (a == cudaSuccess) a = cudaEventCreate(&e->ev0);
     if (a == cudaSuccess) a = cudaEventCreate(&e->ev1);
+    if (a == cudaSuccess) a = cudaEventCreateWithFlags(&e->pstart, cudaEventDisableTiming);
+    for (int p = 0; p < smcb_engine::kParts && a == cudaSuccess; p++) {
+        a = cudaStreamCreateWithFlags(&e->pstream[p], cudaStreamNonBlocking);
+        if (a == cudaSuccess) a = cudaEventCreateWithFlags(&e->pev[p], cudaEventDisableTiming);
+    }
+    if (a == cudaSuccess) a = cudaMallocHost(&e->pairs_pinned, 3 * sizeof(unsigned long long));
     if (a == cudaSuccess) a = e->pos.ensure(3 * cn);
     if (a == cudaSuccess) a = e->E.ensure(nchains);
     if (a == cudaSuccess) a = e->nacc.ensure(nchains);
     if (a == cudaSuccess) a = e->ntri.ensure(nchains);
-    if (a == cudaSuccess) a = e->pairs.ensure(2);
+    if (a == cudaSuccess) a = e->pairs.ensure(3);
     if (a == cudaSuccess) a = e->totals.ensure((size_t)kTot * nchains);
     if (a == cudaSuccess) a = e->rbin.ensure((size_t)nchains * N);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->E.p, 0, nchains * sizeof(double), e->stream);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->nacc.p, 0, nchains * sizeof(long long), e->stream);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->ntri.p, 0, nchains * sizeof(long long), e->stream);
-    if (a == cudaSuccess) a = cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->rbin.p, 0, (size_t)nchains * N * sizeof(int), e->stream);
     if (a == cudaSuccess) a = cudaStreamSynchronize(e->stream);
     if (a != cudaSuccess) {
@@ -195,6 +205,12 @@ int smcb_destroy(smcb_engine *e)
     e->e_wall.release(); e->f_wall.release(); e->totals.release(); e->moments.release();
     e->peak_out.release(); e->fed_a.release(); e->fed_b.release(); e->nacc.release(); e->ntri.release();
     e->cache_out.release(); e->chain_mom.release(); e->eval_partials.release(); e->eval_tickets.release(); e->trace_E.release(); e->trace_acc.release(); e->fed_off.release(); e->pairs.release(); e->counters.release(); e->fed_acc.release(); e->rbin.release();
+    for (int p = 0; p < smcb_engine::kParts; p++) {
+        if (e->pstream[p]) { cudaStreamSynchronize(e->pstream[p]); cudaStreamDestroy(e->pstream[p]); }
+        if (e->pev[p]) cudaEventDestroy(e->pev[p]);
+    }
+    if (e->pstart) cudaEventDestroy(e->pstart);
+    if (e->pairs_pinned) cudaFreeHost(e->pairs_pinned);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -215,15 +231,27 @@ int smcb_device_info(smcb_engine *e, int *sm_count, int *cc_major, int *cc_minor
     return SMCB_OK;
 }
 
-static int obs_alloc(smcb_engine *e)
+// Clear the ACCUMULATORS (counters and moments).  Rbin - the voxel every particle was in at the last gather,
+// localDensityAndMobility's `Rbin`, SMC.c:921-924 - is chain state, not an accumulator: it survives a reset, so the
+// mobility counts of the next accumulation window are those of an uninterrupted run.  with_rbin clears it too (a new
+// parameter set / a new observable configuration: the reference callocs it at the start of sMC, SMC.c:54).
+static int obs_alloc(smcb_engine *e, bool with_rbin)
 {
     CK(e->counters.ensure(e->u64_per_group() * e->ngroups));
     CK(e->moments.ensure(e->f64_per_group() * e->ngroups));
     CK(cudaMemsetAsync(e->counters.p, 0, e->u64_per_group() * e->ngroups * sizeof(unsigned long long), e->stream));
     CK(cudaMemsetAsync(e->moments.p, 0, e->f64_per_group() * e->ngroups * sizeof(double), e->stream));
-    CK(cudaMemsetAsync(e->rbin.p, 0, (size_t)e->C * e->N * sizeof(int), e->stream));
+    if (with_rbin) CK(cudaMemsetAsync(e->rbin.p, 0, (size_t)e->C * e->N * sizeof(int), e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    e->obs_reduced = false;
     return SMCB_OK;
+}
+
+static uint64_t fnv1a(const void *data, size_t n, uint64_t h = 0xcbf29ce484222325ull)
+{
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
 }
 
 int smcb_set_params(smcb_engine *e, const smcb_chain_params *p, int nparams, const double *W, int nwalls, int ngroups)
@@ -252,7 +280,9 @@ int smcb_set_params(smcb_engine *e, const smcb_chain_params *p, int nparams, con
     CK(cudaStreamSynchronize(e->stream));
     e->nparams = nparams; e->nwalls = nwalls; e->ngroups = ngroups;
     e->have_params = true; e->energy_valid = false; e->forces_valid = false;
-    return obs_alloc(e);
+    e->params_hash = fnv1a(p, (size_t)nparams * sizeof(*p));
+    if (W && nwalls > 0) e->params_hash = fnv1a(W, wlen * sizeof(double), e->params_hash);
+    return obs_alloc(e, true);
 }
 
 int smcb_set_positions(smcb_engine *e, const double *R)
@@ -396,13 +426,7 @@ static int refresh_energy(smcb_engine *e, int mode)
     o.totals = e->totals.p;
     int rc = run_evaluate(e, mode, o);
     if (rc) return rc;
-    // E[c] = totals[c][0] + totals[c][1]: strided 2-D copies then an add would need a kernel;
-    // C is small next to a sweep, do it through the host once.
-    std::vector<double> t((size_t)kTot * e->C), E(e->C);
-    CK(cudaMemcpyAsync(t.data(), e->totals.p, t.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    for (int c = 0; c < e->C; c++) E[c] = t[kTot * c] + t[kTot * c + 1];
-    CK(cudaMemcpyAsync(e->E.p, E.data(), E.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(launch_energy_from_totals(e->totals.p, e->E.p, e->C, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->energy_valid = true;
     return SMCB_OK;
@@ -451,7 +475,7 @@ int smcb_reset_counters(smcb_engine *e)
 static int finish_timed(smcb_engine *e, int launches)
 {
     CK(cudaEventRecord(e->ev1, e->stream));
-    CK(cudaMemcpyAsync(e->last_pairs, e->pairs.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->last_pairs, e->pairs.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
     e->last_launches = launches;
@@ -471,8 +495,11 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
     if (e->N > kSweepBlockMaxN)
         return fail(SMCB_ERR_ARG, "sweep kernels support N <= %d (N = %d): use smcb_step_allparticle", kSweepBlockMaxN, e->N);
     if (nsweeps == 0) return SMCB_OK;
-    if (!e->energy_valid && (rc = refresh_energy(e, mode))) return rc;
+    // stale running energy: the FAST warp-per-chain kernels take it from their own cache rebuild, the others need an evaluation
+    const bool kernel_refreshes = mode == SMCB_FAST && e->N <= kSweepMaxN;
+    if (!e->energy_valid && !kernel_refreshes && (rc = refresh_energy(e, mode))) return rc;
     SweepArgs a{};
+    a.refresh_E = (!e->energy_valid && kernel_refreshes) ? 1 : 0;
     a.nsweeps = nsweeps;
     a.rng = RngArgs{(uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->chain0, e->step};
     const size_t sc = (size_t)nsweeps * e->C;
@@ -496,7 +523,7 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
         CK(e->cache_out.ensure((size_t)e->C * 5 * e->Npad));
         a.cache_out = e->cache_out.p;
     }
-    CK(cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     const DevChains d = e->chains();
     a.dense_hint = e->sweep_dense;
@@ -514,6 +541,7 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
     }
     if (!fed) e->step += (uint64_t)nsweeps;
     e->forces_valid = false;
+    e->energy_valid = true;
     return SMCB_OK;
 }
 
@@ -535,6 +563,137 @@ int smcb_sweep_traced(smcb_engine *e, int nsweeps, int mode, const double *displ
     return sweep_common(e, nsweeps, mode, fed, displ, offset, u, nullptr, E_trace, acc_trace);
 }
 
+}  // extern "C"
+
+// ------------------------------------------- the host-buffer step, pipelined
+// One call = upload the chains' positions from the caller's HOST buffer, advance them, (optionally) gather the
+// observables, download positions and chain state.  The batch is cut into kParts blocks of chains, each on its own
+// stream: block p's PCIe copies run while the other blocks' kernels do, so the call costs max(kernels, copies) plus
+// one block's copies instead of their sum.  Page-locked (pinned) host buffers are needed for the overlap; pageable
+// ones work, serialised by the driver.  Results are those of smcb_set_positions + smcb_sweep (or
+// smcb_step_allparticle) + smcb_gather + smcb_get_positions + smcb_get_chain_state on the whole batch: chains are
+// independent and a chain's random stream is a function of its global id only.
+static DevChains sub_chains(smcb_engine *e, int c0, int cn)
+{
+    DevChains d = e->chains();
+    d.C = cn;
+    d.pos += (size_t)c0 * 3 * e->Npad;
+    d.E += c0; d.nacc += c0; d.ntri += c0;
+    if (d.nparams != 1) d.params += c0;
+    return d;
+}
+
+extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, int kernel, int gather,
+                               double *E_out, int64_t *naccept_out, int64_t *ntrials_out)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->have_params) return fail(SMCB_ERR_STATE, "smcb_set_params has not been called");
+    if (!R) return fail(SMCB_ERR_ARG, "R is null");
+    if (nsteps <= 0) return fail(SMCB_ERR_ARG, "nsteps must be positive");
+    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
+    if (kernel != 0 && kernel != 1) return fail(SMCB_ERR_ARG, "kernel: 0 = sweep (oneParticleMoves), 1 = all-particle step");
+    if (kernel == 0 && e->N > kSweepMaxN && mode == SMCB_STRICT)
+        return fail(SMCB_ERR_ARG, "the STRICT (bit-exact) sweep kernel supports N <= %d (N = %d): use SMCB_FAST", kSweepMaxN, e->N);
+    if (kernel == 0 && e->N > kSweepBlockMaxN) return fail(SMCB_ERR_ARG, "sweep kernels support N <= %d (N = %d)", kSweepBlockMaxN, e->N);
+    if (kernel == 1 && (size_t)(6 * e->Npad + 256) * sizeof(double) > 227 * 1024) return fail(SMCB_ERR_ARG, "N = %d does not fit one CTA's shared memory", e->N);
+    if (gather && !e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");
+    if (gather && e->obs_reduced) return fail(SMCB_ERR_STATE, "the observable block holds an all-reduced total: smcb_obs_reset first");
+    const int C = e->C, N = e->N, Npad = e->Npad;
+    const size_t cn3 = (size_t)C * 3 * Npad;
+    CK(e->stage.ensure((size_t)C * 3 * N));
+    if (kernel == 1) { CK(e->F.ensure(cn3)); CK(e->Fn.ensure(cn3)); CK(e->dl.ensure(cn3)); }
+    if (gather) CK(e->chain_mom.ensure((size_t)C * 5));
+    int parts = smcb_engine::kParts;
+    while (parts > 1 && C / parts < 256) parts /= 2;             // small batches: the copies are not worth splitting
+    int eparts = 1;                                               // blocks per chain of the FAST evaluation, decided per block size
+    {
+        DevChains dd = sub_chains(e, 0, (C + parts - 1) / parts);
+        eparts = evaluate_fast_parts(dd);
+    }
+    CK(e->eval_partials.ensure((size_t)C * eparts * kTot));
+    if (e->eval_tickets.n < (size_t)C) {
+        CK(e->eval_tickets.ensure(C));
+        CK(cudaMemsetAsync(e->eval_tickets.p, 0, C * sizeof(unsigned), e->stream));
+    }
+    CK(cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    CK(cudaEventRecord(e->pstart, e->stream));
+    GatherArgs g{};
+    if (gather) {
+        g.totals = e->totals.p; g.rbin = e->rbin.p; g.counters = e->counters.p; g.moments = e->moments.p;
+        g.chain_mom = e->chain_mom.p; g.ngroups = e->ngroups;
+        g.wall_virial_intended = e->wall_virial_intended ? 1 : 0;
+        g.u64_per_group = e->u64_per_group(); g.f64_per_group = e->f64_per_group();
+        g.nebins = e->nebins; g.e_lo = e->e_lo; g.e_hi = e->e_hi;
+    }
+    const bool kernel_refreshes = kernel == 1 || (mode == SMCB_FAST && N <= kSweepMaxN);     // no separate energy evaluation needed
+    for (int p = 0; p < parts; p++) {
+        const int c0 = (int)((long long)C * p / parts), c1 = (int)((long long)C * (p + 1) / parts), cn = c1 - c0;
+        if (cn <= 0) continue;
+        cudaStream_t st = e->pstream[p];
+        CK(cudaStreamWaitEvent(st, e->pstart, 0));
+        const size_t aoff = (size_t)c0 * 3 * N, an = (size_t)cn * 3 * N;
+        DevChains d = sub_chains(e, c0, cn);
+        // in: positions; E <- energy + wallsEnergy of them (SMC.c:48) comes out of the kernel's own cache rebuild
+        CK(cudaMemcpyAsync(e->stage.p + aoff, R + aoff, an * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(launch_aos_to_soa(e->stage.p + aoff, d.pos, cn, N, Npad, 3, st));
+        if (!kernel_refreshes) {             // STRICT / block-per-chain sweeps read d.E: evaluate it first
+            EvalOut o{};
+            o.totals = e->totals.p + (size_t)c0 * kTot;
+            DevChains dev = d;
+            dev.step_scale = 1.0; dev.pair_counts = nullptr;
+            if (mode == SMCB_STRICT) CK(launch_evaluate_strict(dev, o, st));
+            else CK(launch_evaluate_fast_screened(dev, o, eparts, e->eval_partials.p + (size_t)c0 * eparts * kTot, e->eval_tickets.p + c0, st));
+            CK(launch_energy_from_totals(o.totals, d.E, cn, st));
+        }
+        const RngArgs rng{(uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->chain0 + (uint32_t)c0, e->step};
+        if (kernel == 0) {
+            SweepArgs a{};
+            a.nsweeps = nsteps; a.rng = rng; a.dense_hint = e->sweep_dense; a.refresh_E = kernel_refreshes ? 1 : 0;
+            CK(mode == SMCB_STRICT ? launch_sweep_strict(false, d, a, st) : launch_sweep_fast(false, d, a, st));
+        } else {
+            StepArgs a{};
+            a.nsteps = nsteps; a.refresh = 1; a.rng = rng;
+            a.F = e->F.p + (size_t)c0 * 3 * Npad; a.Fn = e->Fn.p + (size_t)c0 * 3 * Npad; a.dl = e->dl.p + (size_t)c0 * 3 * Npad;
+            CK(mode == SMCB_STRICT ? launch_allparticle_strict(false, d, a, st) : launch_allparticle_fast(false, d, a, st));
+        }
+        CK(cudaEventRecord(e->pev[p], st));                  // the block's chains are advanced: the gather may read them
+        CK(cudaStreamWaitEvent(e->stream, e->pev[p], 0));
+        // out: positions and chain state
+        CK(launch_soa_to_aos(d.pos, e->stage.p + aoff, cn, N, Npad, 3, st));
+        CK(cudaMemcpyAsync(R + aoff, e->stage.p + aoff, an * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (E_out) CK(cudaMemcpyAsync(E_out + c0, d.E, cn * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (naccept_out) CK(cudaMemcpyAsync(naccept_out + c0, d.nacc, cn * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        if (ntrials_out) CK(cudaMemcpyAsync(ntrials_out + c0, d.ntri, cn * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    if (gather) {
+        // one evaluation + gather of the WHOLE batch once every block is advanced (a 512-thread evaluation block needs an SM
+        // free of sweep blocks: interleaving it per block with the other blocks' sweeps drained SMs and cost 5 ms); the
+        // blocks' downloads run meanwhile on their own streams
+        EvalOut o{};
+        o.totals = e->totals.p;
+        if ((rc = run_evaluate(e, SMCB_FAST, o))) return rc;
+        CK(launch_gather(e->chains(), g, e->stream));
+    }
+    for (int p = 0; p < parts; p++) {
+        CK(cudaEventRecord(e->pev[p], e->pstream[p]));       // the block's downloads are done
+        CK(cudaStreamWaitEvent(e->stream, e->pev[p], 0));
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(e->pairs_pinned, e->pairs.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    for (int k = 0; k < 3; k++) e->last_pairs[k] = e->pairs_pinned[k];
+    e->last_launches = parts * 3 + (gather ? 3 : 0);
+    if (kernel == 0 && mode == SMCB_FAST) e->sweep_dense = e->last_pairs[1] * 50ull > e->last_pairs[0] ? 1 : 0;
+    e->step += (uint64_t)nsteps;
+    e->have_pos = true; e->energy_valid = true; e->forces_valid = kernel == 1;
+    if (gather) e->totals_valid = true;
+    return SMCB_OK;
+}
+
+extern "C" {
 // ------------------------------------------------------- all-particle step
 static int step_common(smcb_engine *e, int nsteps, int mode, bool fed, const double *xi, const double *u,
                        double *lnap, uint8_t *accepted)
@@ -564,7 +723,7 @@ static int step_common(smcb_engine *e, int nsteps, int mode, bool fed, const dou
     }
     if (lnap) { CK(e->stage.ensure(sc > (size_t)e->C * 3 * e->N ? sc : (size_t)e->C * 3 * e->N)); a.lnap = e->stage.p; }
     if (accepted) { CK(e->fed_acc.ensure(sc)); a.accepted = e->fed_acc.p; }
-    CK(cudaMemsetAsync(e->pairs.p, 0, 2 * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     const DevChains d = e->chains();
     CK(mode == SMCB_STRICT ? launch_allparticle_strict(fed, d, a, e->stream) : launch_allparticle_fast(fed, d, a, e->stream));
@@ -588,6 +747,63 @@ int smcb_step_allparticle(smcb_engine *e, int nsteps, int mode)
     return step_common(e, nsteps, mode, false, nullptr, nullptr, nullptr, nullptr);
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------ step-size control
+extern "C" int smcb_tune_step_size(smcb_engine *e, int kernel, int mode, double target, int rounds, int nsteps_per_round)
+{
+    int rc = need_ready(e);
+    if (rc) return rc;
+    if (kernel != 0 && kernel != 1) return fail(SMCB_ERR_ARG, "kernel: 0 = sweep, 1 = all-particle step");
+    if (!(target > 0.0 && target < 1.0) || rounds <= 0 || nsteps_per_round <= 0)
+        return fail(SMCB_ERR_ARG, "need 0 < target < 1, rounds > 0, nsteps_per_round > 0");
+    if (e->nparams == 1 && e->C > 1) {              // one shared parameter set: give every chain its own copy
+        smcb_chain_params one;
+        CK(cudaMemcpyAsync(&one, e->params.p, sizeof one, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        std::vector<smcb_chain_params> all((size_t)e->C, one);
+        CK(e->params.ensure(e->C));
+        CK(cudaMemcpyAsync(e->params.p, all.data(), all.size() * sizeof one, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->nparams = e->C;
+    }
+    for (int r = 0; r < rounds; r++) {
+        CK(cudaMemsetAsync(e->nacc.p, 0, e->C * sizeof(long long), e->stream));
+        CK(cudaMemsetAsync(e->ntri.p, 0, e->C * sizeof(long long), e->stream));
+        rc = kernel == 0 ? smcb_sweep(e, nsteps_per_round, mode) : smcb_step_allparticle(e, nsteps_per_round, mode);
+        if (rc) return rc;
+        const double gain = std::max(1.0, 3.0 / (1.0 + 0.25 * r));   // decreasing, then constant: A settles where acceptance = target
+        CK(launch_adapt_step(e->params.p, e->nacc.p, e->ntri.p, e->C, target, gain, 1e-14, 1e3, e->stream));
+        e->forces_valid = e->forces_valid && kernel == 1;
+    }
+    std::vector<smcb_chain_params> all((size_t)e->nparams);
+    CK(cudaMemcpyAsync(all.data(), e->params.p, all.size() * sizeof(smcb_chain_params), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    uint64_t h = fnv1a(all.data(), all.size() * sizeof(smcb_chain_params));
+    if (e->nwalls > 0) {
+        std::vector<double> W((size_t)e->nwalls * 2 * e->M * e->M);
+        CK(cudaMemcpyAsync(W.data(), e->W.p, W.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        h = fnv1a(W.data(), W.size() * sizeof(double), h);
+    }
+    e->params_hash = h;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_get_step_sizes(smcb_engine *e, double *A)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!A) return fail(SMCB_ERR_ARG, "A is null");
+    if (!e->have_params) return fail(SMCB_ERR_STATE, "smcb_set_params has not been called");
+    std::vector<smcb_chain_params> all((size_t)e->nparams);
+    CK(cudaMemcpyAsync(all.data(), e->params.p, all.size() * sizeof(smcb_chain_params), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int c = 0; c < e->C; c++) A[c] = all[e->nparams == 1 ? 0 : c].A;
+    return SMCB_OK;
+}
+
+extern "C" {
 // -------------------------------------------------------------- observables
 int smcb_obs_configure(smcb_engine *e, int nebins, double e_lo, double e_hi)
 {
@@ -595,7 +811,7 @@ int smcb_obs_configure(smcb_engine *e, int nebins, double e_lo, double e_hi)
     if (rc) return rc;
     if (nebins <= 0 || !(e_hi > e_lo)) return fail(SMCB_ERR_ARG, "need nebins>0 and e_hi>e_lo");
     e->nebins = nebins; e->e_lo = e_lo; e->e_hi = e_hi;
-    return obs_alloc(e);
+    return obs_alloc(e, true);
 }
 
 int smcb_obs_layout_get(smcb_engine *e, smcb_obs_layout *out)
@@ -620,6 +836,9 @@ int smcb_gather(smcb_engine *e)
     int rc = need_ready(e);
     if (rc) return rc;
     if (!e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");
+    if (e->obs_reduced)
+        return fail(SMCB_ERR_STATE, "the observable block holds an all-reduced total (smcb_obs_allreduce / smcb_obs_import_device): "
+                                    "gathering on top of it would count the other ranks' samples again at the next reduce; call smcb_obs_reset first");
     EvalOut o{};
     o.totals = e->totals.p;
     CK(cudaEventRecord(e->ev0, e->stream));
@@ -644,7 +863,7 @@ int smcb_obs_reset(smcb_engine *e)
 {
     int rc = check(e);
     if (rc) return rc;
-    return obs_alloc(e);
+    return obs_alloc(e, false);
 }
 
 int smcb_obs_get(smcb_engine *e, uint64_t *counters, double *moments)
@@ -713,41 +932,64 @@ std::vector<void *> g_nccl_comms;
 constexpr int kNcclSum = 0, kNcclUint64 = 5, kNcclFloat64 = 8;     // nccl.h: ncclSum, ncclUint64, ncclFloat64
 }  // namespace
 
+static std::mutex g_nccl_mutex;            // guards the communicator cache (g_nccl_comms / g_nccl_devs)
+
 extern "C" int smcb_obs_allreduce(smcb_engine **engines, int n)
 {
     if (!engines || n <= 0) return fail(SMCB_ERR_ARG, "need n > 0 engines");
     for (int i = 0; i < n; i++) {
-        if (!engines[i] || !engines[i]->counters.p) return fail(SMCB_ERR_STATE, "engine %d has no observable block", i);
-        if (engines[i]->u64_per_group() * engines[i]->ngroups != engines[0]->u64_per_group() * engines[0]->ngroups)
-            return fail(SMCB_ERR_ARG, "engine %d has a different observable layout", i);
+        smcb_engine *e = engines[i];
+        if (!e || !e->counters.p) return fail(SMCB_ERR_STATE, "engine %d has no observable block", i);
+        if (e->ngroups != engines[0]->ngroups || e->nebins != engines[0]->nebins || e->u64_per_group() != engines[0]->u64_per_group() ||
+            e->f64_per_group() != engines[0]->f64_per_group() || e->e_lo != engines[0]->e_lo || e->e_hi != engines[0]->e_hi)
+            return fail(SMCB_ERR_ARG, "engine %d has a different observable layout (groups, energy bins or range)", i);
+        if (e->obs_reduced) return fail(SMCB_ERR_STATE, "engine %d already holds an all-reduced block: smcb_obs_reset before reducing again", i);
         for (int j = 0; j < i; j++)
-            if (engines[j]->device == engines[i]->device) return fail(SMCB_ERR_ARG, "engines %d and %d share GPU %d", j, i, engines[i]->device);
+            if (engines[j]->device == e->device) return fail(SMCB_ERR_ARG, "engines %d and %d share GPU %d", j, i, e->device);
     }
     if (n == 1) return SMCB_OK;
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (!g_nccl.load()) return fail(SMCB_ERR_STATE, "NCCL not available (dlopen libnccl.so.2: %s)", dlerror());
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
     std::vector<int> devs(n);
     for (int i = 0; i < n; i++) devs[i] = engines[i]->device;
     if (devs != g_nccl_devs) {
         for (void *c : g_nccl_comms) g_nccl.CommDestroy(c);
         g_nccl_comms.assign(n, nullptr);
         const int rc = g_nccl.CommInitAll(g_nccl_comms.data(), n, devs.data());
-        if (rc != 0) { g_nccl_comms.clear(); g_nccl_devs.clear(); return fail(SMCB_ERR_CUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString(rc)); }
+        if (rc != 0) { g_nccl_comms.clear(); g_nccl_devs.clear(); cudaSetDevice(prev_dev); return fail(SMCB_ERR_CUDA, "ncclCommInitAll: %s", g_nccl.GetErrorString(rc)); }
         g_nccl_devs = devs;
     }
     const size_t ncnt = engines[0]->u64_per_group() * engines[0]->ngroups, nmom = engines[0]->f64_per_group() * engines[0]->ngroups;
     int rc = g_nccl.GroupStart();
-    for (int i = 0; i < n && rc == 0; i++) {
+    cudaError_t cerr = cudaSuccess;
+    for (int i = 0; i < n && rc == 0 && cerr == cudaSuccess; i++) {          // an error leaves the loop, never the open group
         smcb_engine *e = engines[i];
-        CK(cudaSetDevice(e->device));
+        cerr = cudaSetDevice(e->device);
+        if (cerr != cudaSuccess) break;
         rc = g_nccl.AllReduce(e->counters.p, e->counters.p, ncnt, kNcclUint64, kNcclSum, g_nccl_comms[i], e->stream);
         if (rc == 0) rc = g_nccl.AllReduce(e->moments.p, e->moments.p, nmom, kNcclFloat64, kNcclSum, g_nccl_comms[i], e->stream);
     }
     const int rc2 = g_nccl.GroupEnd();
-    if (rc != 0 || rc2 != 0) return fail(SMCB_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(rc != 0 ? rc : rc2));
-    for (int i = 0; i < n; i++) {
-        CK(cudaSetDevice(engines[i]->device));
-        CK(cudaStreamSynchronize(engines[i]->stream));
+    for (int i = 0; i < n && cerr == cudaSuccess; i++) {
+        cerr = cudaSetDevice(engines[i]->device);
+        if (cerr == cudaSuccess) cerr = cudaStreamSynchronize(engines[i]->stream);
     }
+    cudaSetDevice(prev_dev);
+    if (rc != 0 || rc2 != 0) return fail(SMCB_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(rc != 0 ? rc : rc2));
+    if (cerr != cudaSuccess) return fail(SMCB_ERR_CUDA, "smcb_obs_allreduce: %s", cudaGetErrorString(cerr));
+    for (int i = 0; i < n; i++) engines[i]->obs_reduced = true;     // every block now holds the job's totals
+    return SMCB_OK;
+}
+
+// release the cached NCCL communicators (optional; call when no engine will all-reduce again)
+extern "C" int smcb_obs_allreduce_teardown(void)
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    for (void *c : g_nccl_comms) if (c && g_nccl.CommDestroy) g_nccl.CommDestroy(c);
+    g_nccl_comms.clear();
+    g_nccl_devs.clear();
     return SMCB_OK;
 }
 
@@ -805,7 +1047,7 @@ int smcb_checkpoint_save(smcb_engine *e, const char *path)
     if (!f) return fail(SMCB_ERR_ARG, "cannot open %s for writing", path);
     CkptHeader h{};
     memcpy(h.magic, "SMCB200", 8);
-    h.version = 1; h.C = e->C; h.N = e->N; h.M = e->M; h.ngroups = e->ngroups; h.nebins = e->nebins;
+    h.version = 2; h.params_hash = e->params_hash; h.C = e->C; h.N = e->N; h.M = e->M; h.ngroups = e->ngroups; h.nebins = e->nebins;
     h.chain0 = e->chain0; h.pad_ = (uint32_t)e->sweep_dense; h.seed = e->seed; h.step = e->step; h.step_scale = e->step_scale;
     h.e_lo = e->e_lo; h.e_hi = e->e_hi;
     h.n_counters = e->u64_per_group() * e->ngroups; h.n_moments = e->f64_per_group() * e->ngroups;
@@ -833,30 +1075,55 @@ int smcb_checkpoint_load(smcb_engine *e, const char *path)
     FILE *f = fopen(path, "rb");
     if (!f) return fail(SMCB_ERR_ARG, "cannot open %s", path);
     CkptHeader h{};
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SMCB200", 8) != 0 || h.version != 1) {
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SMCB200", 8) != 0 || h.version != 2) {
         fclose(f);
-        return fail(SMCB_ERR_ARG, "%s is not a smcb200 checkpoint (version 1)", path);
+        return fail(SMCB_ERR_ARG, "%s is not a smcb200 checkpoint (version 2)", path);
     }
     if ((int)h.C != e->C || (int)h.N != e->N || (int)h.M != e->M || (int)h.ngroups != e->ngroups) {
         fclose(f);
         return fail(SMCB_ERR_ARG, "checkpoint is for %u chains x N=%u, M=%u, %u groups; engine has %d x N=%d, M=%d, %d groups",
                     h.C, h.N, h.M, h.ngroups, e->C, e->N, e->M, e->ngroups);
     }
+    if (h.params_hash != e->params_hash) {
+        fclose(f);
+        return fail(SMCB_ERR_ARG, "checkpoint was written under different chain parameters / wall tables than smcb_set_params gave this engine");
+    }
+    // every size is recomputed from the engine's own shape; nothing from the file sizes a copy
+    if (h.nebins == 0 || h.nebins > (1u << 20) || !(h.e_hi > h.e_lo)) {
+        fclose(f);
+        return fail(SMCB_ERR_ARG, "checkpoint header: bad energy histogram (%u bins)", h.nebins);
+    }
+    const size_t u64pg = (size_t)2 * SMCB_NCX * SMCB_NCX * SMCB_NCZ + SMCB_NCZ + h.nebins + 1;
+    const size_t n_counters = u64pg * e->ngroups, n_moments = e->f64_per_group() * e->ngroups;
+    if (h.n_counters != n_counters || h.n_moments != n_moments) {
+        fclose(f);
+        return fail(SMCB_ERR_ARG, "checkpoint header: observable block of %llu + %llu elements, expected %zu + %zu",
+                    (unsigned long long)h.n_counters, (unsigned long long)h.n_moments, n_counters, n_moments);
+    }
+    // read the whole body into host memory first: a truncated file changes nothing on the device
+    const size_t C = e->C, N = e->N, Npad = e->Npad;
+    const size_t sz[7] = {C * 3 * Npad * sizeof(double), C * sizeof(double), C * sizeof(long long), C * sizeof(long long),
+                          C * N * sizeof(int), n_counters * sizeof(unsigned long long), n_moments * sizeof(double)};
+    size_t total = 0;
+    for (size_t v : sz) total += v;
+    std::vector<unsigned char> body(total);
+    const size_t got = fread(body.data(), 1, total, f);
+    const bool extra = got == total && fgetc(f) != EOF;
+    fclose(f);
+    if (got != total) return fail(SMCB_ERR_ARG, "checkpoint_load: %s is truncated (%zu of %zu body bytes)", path, got, total);
+    if (extra) return fail(SMCB_ERR_ARG, "checkpoint_load: %s has trailing bytes", path);
     if ((int)h.nebins != e->nebins || h.e_lo != e->e_lo || h.e_hi != e->e_hi) {
         e->nebins = (int)h.nebins; e->e_lo = h.e_lo; e->e_hi = h.e_hi;
-        if ((rc = obs_alloc(e))) { fclose(f); return rc; }
+        if ((rc = obs_alloc(e, true))) return rc;
     }
-    std::vector<unsigned char> buf;
-    int w = get(f, e->pos.p, (size_t)e->C * 3 * e->Npad, e->stream, buf);
-    if (!w) w = get(f, e->E.p, (size_t)e->C, e->stream, buf);
-    if (!w) w = get(f, e->nacc.p, (size_t)e->C, e->stream, buf);
-    if (!w) w = get(f, e->ntri.p, (size_t)e->C, e->stream, buf);
-    if (!w) w = get(f, e->rbin.p, (size_t)e->C * e->N, e->stream, buf);
-    if (!w) w = get(f, e->counters.p, (size_t)h.n_counters, e->stream, buf);
-    if (!w) w = get(f, e->moments.p, (size_t)h.n_moments, e->stream, buf);
-    fclose(f);
-    if (w == -1) return fail(SMCB_ERR_CUDA, "checkpoint_load: device copy failed");
-    if (w) return fail(SMCB_ERR_ARG, "checkpoint_load: %s is truncated", path);
+    void *dst[7] = {e->pos.p, e->E.p, e->nacc.p, e->ntri.p, e->rbin.p, e->counters.p, e->moments.p};
+    size_t off = 0;
+    for (int k = 0; k < 7; k++) {
+        CK(cudaMemcpyAsync(dst[k], body.data() + off, sz[k], cudaMemcpyHostToDevice, e->stream));
+        off += sz[k];
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    e->obs_reduced = false;
     e->seed = h.seed; e->chain0 = h.chain0; e->step = h.step; e->step_scale = h.step_scale;
     e->sweep_dense = h.pad_ == 1u ? 1 : 0;      // the resumed run launches the kernel the saved run would have launched next
     e->have_pos = true; e->energy_valid = true; e->forces_valid = false;
@@ -877,6 +1144,13 @@ int smcb_last_pair_counts(smcb_engine *e, uint64_t *pairs_total, uint64_t *pairs
     if (!e) return fail(SMCB_ERR_ARG, "null engine");
     if (pairs_total) *pairs_total = e->last_pairs[0];
     if (pairs_in_cutoff) *pairs_in_cutoff = e->last_pairs[1];
+    return SMCB_OK;
+}
+
+int smcb_last_pair_tests(smcb_engine *e, uint64_t *pair_tests_executed)
+{
+    if (!e) return fail(SMCB_ERR_ARG, "null engine");
+    if (pair_tests_executed) *pair_tests_executed = e->last_pairs[2];
     return SMCB_OK;
 }
 

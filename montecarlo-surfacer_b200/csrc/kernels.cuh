@@ -30,7 +30,9 @@ struct DevChains {
     double *E;                // [C] running potential energy
     long long *nacc, *ntri;   // [C]
     double step_scale;        // A multiplier (thermalisation uses 2, SMC.c:110)
-    unsigned long long *pair_counts;   // [0] ordered pairs evaluated, [1] of them inside the cutoff
+    unsigned long long *pair_counts;   // [0] ordered pair-interactions as the reference executes them (nominal), [1] of them inside
+                                       // the cutoff, [2] pair distance tests the kernel actually EXECUTED (cached / screened / half-shell
+                                       // kernels execute fewer than [0])
 };
 
 constexpr int kTot = 5;      // chain totals: U_lj, U_wall, vir_lj, vir_wall_ref (as the reference writes it), vir_wall (as it meant it)
@@ -55,6 +57,7 @@ struct SweepArgs {
     double *cache_out;         // test hook of the cached kernel, nullable: [C][5][Npad]
     double *trace_E;           // nullable [s][C]: running energy after every sweep (sMC's E[n+1], SMC.c:116,194)
     int *trace_acc;            // nullable [s][C]: accepted trials of every sweep (sMC's jj[n])
+    int refresh_E;             // 1: d.E is stale - the FAST warp kernels take the chain energy from their cache rebuild (SMC.c:48)
     int dense_hint;            // host side only: 1 = the previous launch found > 2 % of the pairs inside the cutoff (condensed phase)
 };
 
@@ -447,6 +450,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
         if (d.pair_counts) {
             atomicAdd(d.pair_counts, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));
             atomicAdd(d.pair_counts + 1, tot);
+            atomicAdd(d.pair_counts + 2, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));    // two full passes per trial
         }
     }
 }
@@ -576,6 +580,7 @@ __global__ void k_allparticle(DevChains d, StepArgs a)
         if (d.pair_counts) {
             atomicAdd(d.pair_counts, (unsigned long long)a.nsteps * (unsigned long long)N * (N - 1));
             atomicAdd(d.pair_counts + 1, (unsigned long long)c[0]);
+            atomicAdd(d.pair_counts + 2, (unsigned long long)(a.nsteps + (a.refresh ? 1 : 0)) * (unsigned long long)N * (N - 1));
         }
     }
 }
@@ -690,6 +695,30 @@ __global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict_
         for (int k = 0; k < ncomp; k++)
             aos[(c * N + j) * ncomp + k] = soa[(c * ncomp + k) * Npad + j];
     }
+}
+
+// E[c] = U_lj + U_wall of the last evaluation (SMC.c:48: E[0] = energy(R) + wallsEnergy(R)), on the device
+__global__ void k_energy_from_totals(const double *__restrict__ totals, double *__restrict__ E, int C)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) E[c] = totals[(size_t)c * kTot] + totals[(size_t)c * kTot + 1];
+}
+
+// step-size control (pre-production only): A[c] *= exp(gain * (acceptance[c] - target)), counters cleared
+__global__ void k_adapt_step(smcb_chain_params *params, long long *nacc, long long *ntri, int C, double target, double gain,
+                             double a_min, double a_max)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const long long t = ntri[c];
+    if (t > 0) {
+        const double acc = (double)nacc[c] / (double)t;
+        // nothing / everything accepted says only "far off": move by a decade / a factor of four instead of the gain's e-fold
+        double A = params[c].A * (nacc[c] == 0 ? 0.1 : (nacc[c] == t ? 4.0 : exp(gain * (acc - target))));
+        A = A < a_min ? a_min : (A > a_max ? a_max : A);
+        params[c].A = A;
+    }
+    nacc[c] = 0; ntri[c] = 0;
 }
 
 // FP64 FMA peak: 8 independent DFMA chains per thread, no memory traffic

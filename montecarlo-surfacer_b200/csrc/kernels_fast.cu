@@ -34,6 +34,31 @@ cudaError_t launch_soa_to_aos(const double *soa, double *aos, int C, int N, int 
     return cudaGetLastError();
 }
 
+cudaError_t launch_energy_from_totals(const double *totals, double *E, int C, cudaStream_t st)
+{
+    k_energy_from_totals<<<(C + 255) / 256, 256, 0, st>>>(totals, E, C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_chains(const DevChains &d, const GatherArgs &g, cudaStream_t st)      // per-chain part only
+{
+    k_gather<<<d.C, 128, 0, st>>>(d, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_moments(const DevChains &d, const GatherArgs &g, cudaStream_t st)     // per-group sums, all chains
+{
+    k_gather_moments<<<g.ngroups, 256, 0, st>>>(d, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adapt_step(smcb_chain_params *params, long long *nacc, long long *ntri, int C, double target, double gain,
+                              double a_min, double a_max, cudaStream_t st)
+{
+    k_adapt_step<<<(C + 255) / 256, 256, 0, st>>>(params, nacc, ntri, C, target, gain, a_min, a_max);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dfma_peak(double *out, int blocks, int threads, int iters, cudaStream_t st)
 {
     k_dfma_peak<<<blocks, threads, 0, st>>>(out, iters, 1.0);

@@ -17,6 +17,11 @@ cudaError_t launch_evaluate_strict(const DevChains &d, const EvalOut &o, cudaStr
 int evaluate_fast_parts(const DevChains &d);
 cudaError_t launch_evaluate_fast_screened(const DevChains &d, const EvalOut &o, int parts, double *partials, unsigned *tickets, cudaStream_t st);
 cudaError_t launch_gather(const DevChains &d, const GatherArgs &g, cudaStream_t st);
+cudaError_t launch_gather_chains(const DevChains &d, const GatherArgs &g, cudaStream_t st);
+cudaError_t launch_gather_moments(const DevChains &d, const GatherArgs &g, cudaStream_t st);
+cudaError_t launch_adapt_step(smcb_chain_params *params, long long *nacc, long long *ntri, int C, double target, double gain,
+                              double a_min, double a_max, cudaStream_t st);
+cudaError_t launch_energy_from_totals(const double *totals, double *E, int C, cudaStream_t st);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, int C, int N, int Npad, int ncomp, cudaStream_t st);
 cudaError_t launch_soa_to_aos(const double *soa, double *aos, int C, int N, int Npad, int ncomp, cudaStream_t st);
 cudaError_t launch_dfma_peak(double *out, int blocks, int threads, int iters, cudaStream_t st);

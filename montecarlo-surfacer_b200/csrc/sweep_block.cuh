@@ -215,6 +215,7 @@ __device__ __forceinline__ void sweep_block_body(const DevChains &d, const Sweep
         if (d.pair_counts) {
             atomicAdd(d.pair_counts, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));
             atomicAdd(d.pair_counts + 1, (unsigned long long)c[0]);
+            atomicAdd(d.pair_counts + 2, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));    // no caches: old + proposed position
         }
     }
 }

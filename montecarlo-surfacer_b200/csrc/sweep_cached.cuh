@@ -245,11 +245,12 @@ __device__ __forceinline__ void add_zwall(const Box &b, double dzw, double &e, d
 template <int K, bool PZ>
 __device__ __forceinline__ void eval_point(const Box &b, const ScreenConsts &sc, const ChainSmem &s, int lane, int MMpad,
                                            unsigned okmask, double px, double py, double pz, const Slots<K> &q,
-                                           double &U, double &Fx, double &Fy, double &Fz, unsigned &in)
+                                           double &U, double &Fx, double &Fy, double &Fz, unsigned &in, double *Upair = nullptr)
 {
     unsigned hits = screen_slots<K, PZ>(sc, (float)(px * b.invL), (float)(py * b.invL), (float)(pz * b.invL), q) & okmask;
     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
     in = add_hits(b, s, lane, hits, px, py, pz, e, fx, fy, fz);
+    if (Upair) *Upair = 4.0 * warp_sum(e);          // energySingle alone: the chain energy counts every pair once (SMC.c:626-646)
     double dzw = 0.0;
     if (b.wall) {
         dzw = wall_dz<false>(b, pz);
@@ -301,11 +302,13 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
     const ScreenConsts sc = make_screen(b);
 
     // ---- rebuild the caches from the positions ------------------------------------
+    double Erebuilt = 0.0;
     for (int n = 0; n < N; n++) {
         const unsigned okmask = validmask & ~(((n & 31) == lane) ? (1u << (n >> 5)) : 0u);
-        double U, Fx, Fy, Fz;
+        double U, Fx, Fy, Fz, Up;
         unsigned in;
-        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], q, U, Fx, Fy, Fz, in);
+        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], q, U, Fx, Fy, Fz, in, &Up);
+        Erebuilt += U - 0.5 * Up;                    // energy(R) + wallsEnergy(R), SMC.c:48
         const int cntn = __reduce_add_sync(FULL, __popc(in));
         if (lane == 0) { s.ce[n] = U; s.cfx[n] = Fx; s.cfy[n] = Fy; s.cfz[n] = Fz; s.nb[n] = (unsigned short)cntn; }
     }
@@ -314,10 +317,11 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
     const double AoT = b.A / b.T;
     const double sigma = sqrt(2.0 * b.A);            // vecBoxMuller(sqrt(2.0*A), ...)  SMC.c:284
     const double quarterAoT = 0.25 * AoT, invT = 1.0 / b.T;
-    double E = d.E[chain];
+    double E = a.refresh_E ? Erebuilt : d.E[chain];
     double dE = 0.0;                                 // per-lane share of the running energy (speculative path)
     int nacc = 0;
     unsigned cnt = 0;                                // per-lane, < 2^32 per launch
+    unsigned nscr = (unsigned)N;                     // N-particle screens executed (warp-uniform); the cache rebuild ran N
     const RngId id{a.rng.k0, a.rng.k1, a.rng.chain0 + (uint32_t)chain};
 
     // Physical register slot 0 always holds the slot that is being visited: the visiting
@@ -419,6 +423,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                 auto drop_old_partners = [&](int m, unsigned okm) -> bool {
                     const double px = s.x[m], py = s.y[m], pz = s.z[m];
                     unsigned ho = screen_slots<K, PZ>(sc, (float)(px * b.invL), (float)(py * b.invL), (float)(pz * b.invL), q) & okm;
+                    nscr++;
                     bool touched = false;
                     while (ho) {
                         const int k = __ffs(ho) - 1;
@@ -444,6 +449,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                         // ---- one screen of the lane's K slots against the staged proposal
                         qsx = s.stage[t]; qsy = s.stage[32 + t]; qsz = s.stage[64 + t];
                         hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
+                        nscr++;
                         if (!__any_sync(FULL, hits_new != 0)) {
                             const bool facc = (acc0 >> t) & 1u;
                             if (lane == 0) cnt += nbm;   // in-cutoff pairs of the old position (the reference evaluates them)
@@ -493,6 +499,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
                             add_zwall(b, dzw, ew, fzw);
                         }
                         hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
+                        nscr++;
                     }
 
                     // gas-phase fast path: nobody in range of the proposal -> all pair and site sums are exactly 0
@@ -608,6 +615,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
         if (d.pair_counts) {
             atomicAdd(d.pair_counts, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));
             atomicAdd(d.pair_counts + 1, tot);
+            atomicAdd(d.pair_counts + 2, (unsigned long long)nscr * (unsigned long long)(N - 1));
         }
     }
 }

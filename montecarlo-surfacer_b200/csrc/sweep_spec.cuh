@@ -88,11 +88,13 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
     const ScreenConsts sc = make_screen(b);
 
     // ---- rebuild the caches from the positions ------------------------------------
+    double Erebuilt = 0.0;
     for (int n = 0; n < N; n++) {
         const unsigned okmask = validmask & ~(((n & 31) == lane) ? (1u << (n >> 5)) : 0u);
-        double U, Fx, Fy, Fz;
+        double U, Fx, Fy, Fz, Up;
         unsigned in;
-        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], q, U, Fx, Fy, Fz, in);
+        eval_point<K, PZ>(b, sc, s, lane, MMpad, okmask, s.x[n], s.y[n], s.z[n], q, U, Fx, Fy, Fz, in, &Up);
+        Erebuilt += U - 0.5 * Up;                    // energy(R) + wallsEnergy(R), SMC.c:48
         const int cntn = __reduce_add_sync(FULL, __popc(in));
         if (lane == 0) { s.ce[n] = U; s.cfx[n] = Fx; s.cfy[n] = Fy; s.cfz[n] = Fz; s.nb[n] = (unsigned short)cntn; }
     }
@@ -101,10 +103,11 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
     const double AoT = b.A / b.T;
     const double sigma = sqrt(2.0 * b.A);            // vecBoxMuller(sqrt(2.0*A), ...)  SMC.c:284
     const double quarterAoT = 0.25 * AoT, invT = 1.0 / b.T;
-    double E = d.E[chain];
+    double E = a.refresh_E ? Erebuilt : d.E[chain];
     double dE = 0.0;                                 // per-lane share of the running energy (owner-committed trials)
     int nacc = 0;
     unsigned cnt = 0;                                // per-lane, < 2^32 per launch
+    unsigned nscr = (unsigned)N;                     // N-particle screens executed (warp-uniform); the cache rebuild ran N
     const RngId id{a.rng.k0, a.rng.k1, a.rng.chain0 + (uint32_t)chain};
 
     // physical register slot 0 always holds the slot being visited (see k_sweep_cached): `rot` = logical slot at physical 0
@@ -196,6 +199,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     // no votes in this loop: a lane records what concerns ITS particle / proposal (the relations are symmetric),
                     // and the rare hit masks go to the 32x32 table with an atomicOr on the trial's row word
                     const float MGs = 12582912.f;
+                    nscr += (unsigned)((te - (tb & ~1) + 1) & ~1);
                     for (int t2 = tb & ~1; t2 < te; t2 += 2) {
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
@@ -260,6 +264,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                 auto drop_old_partners = [&](int m, unsigned okm) -> bool {
                     const double px = s.x[m], py = s.y[m], pz = s.z[m];
                     unsigned ho = screen_slots<K, PZ>(sc, (float)(px * b.invL), (float)(py * b.invL), (float)(pz * b.invL), q) & okm;
+                    nscr++;
                     bool touched = false;
                     while (ho) {
                         const int k = __ffs(ho) - 1;
@@ -368,6 +373,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                         }
                     }
                     unsigned hits_new = screen_slots<K, PZ>(sc, qsx, qsy, qsz, q) & okmask;
+                    nscr++;
 
                     double e = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
                     double le = 0.0, lx = 0.0, ly = 0.0, lz = 0.0;
@@ -493,6 +499,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
         if (d.pair_counts) {
             atomicAdd(d.pair_counts, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));
             atomicAdd(d.pair_counts + 1, tot);
+            atomicAdd(d.pair_counts + 2, (unsigned long long)nscr * (unsigned long long)(N - 1));
         }
     }
 }

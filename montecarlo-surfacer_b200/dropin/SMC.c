@@ -360,69 +360,164 @@ void localDensityAndMobility_nonuniz(const double *r, double L, double Lz, doubl
     }
 }
 
-/* Common-neighbour analysis over all pairs l>i (index (l-1)(l-2)/2 + i): LCA[3p] = bonded,
- * LCA[3p+1] = neighbours shared by the pair, LCA[3p+2] = bonds among consecutive shared
- * neighbours.  Host-side, off the GPU path (sampled every LCA_TIME gathers). */
+/* Common-neighbour analysis AS THE REFERENCE COMPUTES IT (SMC.c:971-1045), so that LCA[] is the array the
+ * reference would fill, entry for entry.  For every pair l > i it records: bonded (distance below LCA_cutoff,
+ * minimum image in x,y), how many particles q < l are bonded to both, and how many consecutive ones of those are
+ * bonded to each other.  The reference addresses pair (l,i) at slot (l-1)(l-2)/2 + i, which makes the LAST slot of
+ * row l also the FIRST slot of row l+1, never clears a slot, looks the (q,i) bond up at (q-1)(q-2)/2 + i even when
+ * i > q, and keeps appending to one 8-entry scratch list per slot; all of that decides what ends up in LCA[], so it
+ * is kept: slot arithmetic below is the reference's, written once in `slot_of`.  (Host-side and off the GPU path:
+ * sMC samples it every LCA_TIME gathers, and SURVEY App. B6 explains why the numbers sMC derives from it are of
+ * little use.)  The scratch list is bounded here; the reference overruns its own beyond 8 shared neighbours. */
+static inline long slot_of(long hi, long lo) { return (hi * hi - 3 * hi + 2) / 2 + lo; }
+
 void clusterAnalysis(const double *r, int N_, double L, int *LCA)
 {
-    const size_t npairs = (size_t)N_ * (N_ - 1) / 2;
-    unsigned char *bond = calloc((size_t)N_ * N_, 1);
+    const long nslots = ((long)N_ * N_ - N_) / 2;
+    unsigned char *bonded = calloc((size_t)nslots, 1);
+    int *shared = calloc((size_t)nslots, sizeof(int));
+    int *linked = calloc((size_t)nslots, sizeof(int));
+    int list[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int l = 1; l < N_; l++)
         for (int i = 0; i < l; i++) {
-            double dx = r[3 * l] - r[3 * i], dy = r[3 * l + 1] - r[3 * i + 1];
+            double dx = r[3 * l] - r[3 * i];
+            dx = dx - L * rint(dx / L);
+            double dy = r[3 * l + 1] - r[3 * i + 1];
+            dy = dy - L * rint(dy / L);
             const double dz = r[3 * l + 2] - r[3 * i + 2];
-            dx -= L * rint(dx / L);
-            dy -= L * rint(dy / L);
-            if (dx * dx + dy * dy + dz * dz < LCA_cutoff * LCA_cutoff) bond[(size_t)l * N_ + i] = bond[(size_t)i * N_ + l] = 1;
+            if (dx * dx + dy * dy + dz * dz < LCA_cutoff * LCA_cutoff) bonded[slot_of(l, i)] = 1;
         }
-    memset(LCA, 0, 3 * npairs * sizeof(int));
     for (int l = 1; l < N_; l++)
         for (int i = 0; i < l; i++) {
-            const size_t p = (size_t)(l - 1) * (l - 2) / 2 + i;
-            if (!bond[(size_t)l * N_ + i]) continue;
-            int shared[8], ns = 0, chain = 0;
-            for (int q = 0; q < l; q++)
-                if (q != i && bond[(size_t)l * N_ + q] && bond[(size_t)i * N_ + q]) {
-                    if (ns < 8) shared[ns] = q;
-                    ns++;
+            const long s = slot_of(l, i);
+            if (!bonded[s]) continue;
+            for (int q = 0; q < l; q++) {
+                if (q == i) continue;
+                if (bonded[slot_of(l, q)] & bonded[slot_of(q, i)]) {
+                    if (shared[s] < 8) list[shared[s]] = q;
+                    shared[s]++;
                 }
-            for (int m = 1; m < ns && m < 8; m++) chain += bond[(size_t)shared[m] * N_ + shared[m - 1]];
-            if (ns > 6) printf("LCA cutoff might be too big, clustering data will be corrupted\n");
-            LCA[3 * p] = 1; LCA[3 * p + 1] = ns; LCA[3 * p + 2] = chain;
+            }
+            for (int m = 1; m < shared[s] && m < 8; m++)
+                if (bonded[slot_of(list[m], list[m - 1])]) linked[s]++;
         }
-    free(bond);
+    for (long n = 0; n < nslots; n++) {
+        if (shared[n] > 6) printf("LCA cutoff might be too big, clustering data will be corrupted\n");
+        LCA[3 * n] = bonded[n]; LCA[3 * n + 1] = shared[n]; LCA[3 * n + 2] = linked[n];
+    }
+    free(bonded); free(shared); free(linked);
 }
 
 /* ------------------------------------------------------- autocorrelation (SMC.c:1055-1142) ------- */
-/* normalised autocorrelation rho(k) = sum_i z_i z_{i+k} / sum_i z_i^2, k < k_max, by direct sums
- * (the reference's arithmetic lives in FFTW3, an un-vendored dependency: parity unpinned, off the
- * hot path).  k_max is reduced like the reference when the series is short, and capped so the
- * direct sums stay below ~2e9 products. */
+/* The reference's fft_acf hands FFTW (an un-vendored dependency, version unpinned) a real-to-complex plan of the
+ * mean-free series, keeps the first lfft = length/2 (+1 if odd) bins F_j, and takes a COMPLEX backward transform of
+ * length lfft of |F_j|^2 (SMC.c:1067-1085):  acf[k] = Re sum_{j<lfft} |F_j|^2 e^{+2 pi i jk/lfft} / sum_j |F_j|^2.
+ * (With half the spectrum on half the length, entry k is the circular autocorrelation at lag 2k up to an end-bin
+ * term - a quirk of the reference that plotting.jl and tau = sum(acf) inherit, kept.)  FFTW's arithmetic is
+ * restated here by its definition, the discrete Fourier transform, evaluated in O(n log n) for ANY length with
+ * Bluestein's chirp-z identity over a power-of-two FFT: the reference's 16e6-sweep series are transformed whole,
+ * not truncated.  tests/test_postproc_parity.py pins it against the reference's fft_acf to 1e-10. */
+typedef struct { double re, im; } cplx;
+
+static void fft_pow2(cplx *a, size_t n, int sign)            /* in place, n a power of two, e^{sign 2 pi i jk/n} */
+{
+    for (size_t i = 1, j = 0; i < n; i++) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { const cplx t = a[i]; a[i] = a[j]; a[j] = t; }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t half = len >> 1;
+        const double w0 = sign * 6.283185307179586476925286766559 / (double)len;
+        for (size_t k = 0; k < half; k++) {
+            const double wr = cos(w0 * (double)k), wi = sin(w0 * (double)k);
+            for (size_t s0 = k; s0 < n; s0 += len) {
+                cplx *u = a + s0, *v = a + s0 + half;
+                const double xr = v->re * wr - v->im * wi, xi = v->re * wi + v->im * wr;
+                v->re = u->re - xr; v->im = u->im - xi;
+                u->re += xr; u->im += xi;
+            }
+        }
+    }
+}
+
+/* out[k] = sum_j in[j] e^{sign 2 pi i jk/n}, k < nout, for any n: jk = (j^2 + k^2 - (k-j)^2)/2 turns the sum into a
+ * convolution with the chirp c_m = e^{sign pi i m^2/n} (phases from m^2 mod 2n, exact in integers) */
+static int dft_any(const cplx *in, size_t n, int sign, cplx *out, size_t nout)
+{
+    if (n == 0) return 0;
+    size_t m = 1;
+    while (m < 2 * n - 1) m <<= 1;
+    cplx *chirp = malloc(n * sizeof(cplx)), *x = calloc(m, sizeof(cplx)), *y = calloc(m, sizeof(cplx));
+    if (!chirp || !x || !y) { free(chirp); free(x); free(y); return -1; }
+    const unsigned long long two_n = 2ull * n;
+    for (size_t j = 0; j < n; j++) {
+        const unsigned long long q = ((unsigned long long)j * j) % two_n;
+        const double ang = sign * 3.1415926535897932384626433832795 * (double)q / (double)n;
+        chirp[j].re = cos(ang); chirp[j].im = sin(ang);
+    }
+    for (size_t j = 0; j < n; j++) {                         /* x_j = in_j c_j ;  y_j = conj(c_j), wrapped */
+        x[j].re = in[j].re * chirp[j].re - in[j].im * chirp[j].im;
+        x[j].im = in[j].re * chirp[j].im + in[j].im * chirp[j].re;
+        y[j].re = chirp[j].re; y[j].im = -chirp[j].im;
+        if (j) y[m - j] = y[j];
+    }
+    fft_pow2(x, m, -1);
+    fft_pow2(y, m, -1);
+    for (size_t j = 0; j < m; j++) {
+        const double pr = x[j].re * y[j].re - x[j].im * y[j].im, pi = x[j].re * y[j].im + x[j].im * y[j].re;
+        x[j].re = pr; x[j].im = pi;
+    }
+    fft_pow2(x, m, +1);
+    for (size_t k = 0; k < nout && k < n; k++) {             /* out_k = c_k (x * y)_k / m */
+        const double vr = x[k].re / (double)m, vi = x[k].im / (double)m;
+        out[k].re = vr * chirp[k].re - vi * chirp[k].im;
+        out[k].im = vr * chirp[k].im + vi * chirp[k].re;
+    }
+    free(chirp); free(x); free(y);
+    return 0;
+}
+
 DoubleArray fft_acf(const double *H, size_t length, int k_max)
 {
     DoubleArray acf;
     if (length < (size_t)k_max * 2 + 1) {
-        k_max = (int)(length / 2) - 2;
+        k_max = (int)rint((double)(length / 2)) - 2;
         printf("Number of datapoints too low to calculate autocorrelation, new k_max: %d\n", k_max);
     }
     if (k_max < 1) k_max = 1;
-    if ((double)k_max * (double)length > 2e9) k_max = (int)(2e9 / (double)length);
     acf.length = (size_t)k_max;
     acf.data = calloc((size_t)k_max, sizeof(double));
-    simple_acf(H, length, k_max, acf.data);
+    const size_t lfft = length / 2 + length % 2;
+    cplx *z = malloc((length ? length : 1) * sizeof(cplx)), *f = malloc((lfft ? lfft : 1) * sizeof(cplx)), *c = malloc((lfft ? lfft : 1) * sizeof(cplx));
+    if (!acf.data || !z || !f || !c || lfft == 0) { free(z); free(f); free(c); return acf; }
+    const double meanH = mean(H, length);
+    for (size_t i = 0; i < length; i++) { z[i].re = H[i] - meanH; z[i].im = 0.0; }
+    int bad = dft_any(z, length, -1, f, lfft);               /* the bins the r2c plan writes into lfft slots */
+    for (size_t j = 0; j < lfft; j++) { f[j].re = f[j].re * f[j].re + f[j].im * f[j].im; f[j].im = 0.0; }
+    if (!bad) bad = dft_any(f, lfft, +1, c, lfft);           /* FFTW_BACKWARD, unnormalised */
+    if (!bad)
+        for (int k = 0; k < k_max && (size_t)k < lfft; k++) acf.data[k] = c[k].re / c[0].re;
+    else
+        fprintf(stderr, "fft_acf: out of memory for a series of %zu points\n", length);
+    free(z); free(f); free(c);
     return acf;
 }
 
+/* the reference's direct-sum variant (SMC.c:1094-1121), kept for its callers: sums over i < length-k_max-1 for
+ * every lag, normalised by the lag-0 value */
 void simple_acf(const double *H, size_t length, int k_max, double *acf)
 {
+    if (length < (size_t)k_max * 2) perror("error: number of datapoints too low to calculate autocorrelation");
     const double m = mean(H, length);
-    double c0 = 0.0;
-    for (size_t i = 0; i < length; i++) c0 += (H[i] - m) * (H[i] - m);
+    const long upto = (long)length - k_max - 1;
     for (int k = 0; k < k_max; k++) {
         double c = 0.0;
-        for (size_t i = 0; i + (size_t)k < length; i++) c += (H[i] - m) * (H[i + k] - m);
-        acf[k] = c0 > 0 ? c / c0 : (k == 0 ? 1.0 : 0.0);
+        for (long i = 0; i < upto; i++) c += (H[i] - m) * (H[i + k] - m);
+        acf[k] = c / (double)((long)length - k_max);
     }
+    for (int k = k_max - 1; k >= 0; k--) acf[k] = acf[k] / acf[0];
 }
 
 /* variance of every tau-th sample (decorrelated subsample) */
@@ -604,7 +699,10 @@ struct Sim sMC(double L, double Lz, double T, double A, const double *W, const d
         for (int k = 0; k < gather_steps; k++) fprintf(data, "%0.9lf, %0.9lf, %d\n", E[(size_t)k * gather_lapse], P[k], jj[k]);
     SMCB_DO(smcb_obs_get(h, cnt, NULL));
     dump_voxels(local, cnt, cnt + Nc, NULL, NULL);
-    if (total_clusters) fprintf(total_clusters, "%0.9f, %0.9f, %0.9f\n", l1, l2[1], l3[1]);
+    /* the reference opens total_clusters_*.csv, writes its header and reports the numbers on stdout only (SMC.c:92, 226-231) */
+    printf("l1[1] = %0.9f\n", l1);
+    printf("l2[0] = %0.9f\tl2[1] = %0.9f\tl2[2] = %0.9f\tl2[3] = %0.9f\tl2[4] = %0.9f\tl2[5] = %0.9f\n", l2[0], l2[1], l2[2], l2[3], l2[4], l2[5]);
+    printf("l3[0] = %0.9f\tl3[1] = %0.9f\tl3[2] = %0.9f\tl3[3] = %0.9f\tl3[4] = %0.9f\tl3[5] = %0.9f\n", l3[0], l3[1], l3[2], l3[3], l3[4], l3[5]);
 
     DoubleArray acf = fft_acf(E, (size_t)maxsteps + 1, KMAX);
     const double tau = sum(acf.data, acf.length);

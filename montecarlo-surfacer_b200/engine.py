@@ -112,6 +112,11 @@ def load_library():
         "smcb_checkpoint_load": [P, C.c_char_p],
         "smcb_last_kernel_ms": [P, C.POINTER(C.c_float), C.POINTER(C.c_int)],
         "smcb_last_pair_counts": [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+        "smcb_last_pair_tests": [P, C.POINTER(C.c_uint64)],
+        "smcb_sweep_host": [P, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P],
+        "smcb_obs_allreduce_teardown": [],
+        "smcb_tune_step_size": [P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int],
+        "smcb_get_step_sizes": [P, P],
         "smcb_measure_fp64_peak": [P, dp, C.POINTER(C.c_float)],
         "smcb_device_positions": [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)],
         "smcb_debug_capture_cache": [P, C.c_int],
@@ -269,6 +274,19 @@ class Engine:
     def sweep(self, nsweeps, mode=FAST):
         self._ck(self.lib.smcb_sweep(self._h, nsweeps, mode))
 
+    def sweep_host(self, R, nsteps, mode=FAST, kernel="sweep", gather=False, E=None, naccept=None, ntrials=None):
+        """smcb_sweep_host: R (host, [C, 3N] float64, C-contiguous, ideally pinned) is uploaded, advanced nsteps sweeps
+        (kernel="sweep") or all-particle steps ("allparticle"), optionally gathered, and overwritten IN PLACE with the
+        new positions; E / naccept / ntrials (optional preallocated arrays) receive the chain state.  Copies and
+        kernels of the four chain blocks overlap."""
+        if not (isinstance(R, np.ndarray) and R.dtype == np.float64 and R.flags.c_contiguous and R.size == self.C * 3 * self.N):
+            raise ValueError("R must be a C-contiguous float64 array of nchains*3N elements (it is updated in place)")
+        for arr, dt in ((E, np.float64), (naccept, np.int64), (ntrials, np.int64)):
+            if arr is not None and not (arr.dtype == dt and arr.flags.c_contiguous and arr.size == self.C):
+                raise ValueError("chain-state outputs must be contiguous arrays of nchains elements")
+        self._ck(self.lib.smcb_sweep_host(self._h, _ptr(R), nsteps, mode, 0 if kernel == "sweep" else 1, 1 if gather else 0,
+                                          _ptr(E), _ptr(naccept), _ptr(ntrials)))
+
     def sweep_traced(self, nsweeps, mode=FAST, displ=None, offset=None, u=None):
         """(E_trace [S,C], acc_trace [S,C]): sMC's E[n+1] and jj[n] of every sweep"""
         Et = np.empty((nsweeps, self.C))
@@ -292,6 +310,13 @@ class Engine:
 
     def step_allparticle(self, nsteps, mode=FAST):
         self._ck(self.lib.smcb_step_allparticle(self._h, nsteps, mode))
+
+    def tune_step_size(self, kernel="sweep", mode=FAST, target=0.5, rounds=8, nsteps_per_round=10):
+        """smcb_tune_step_size: per-chain A adapted towards the target acceptance; returns the A array"""
+        self._ck(self.lib.smcb_tune_step_size(self._h, 0 if kernel == "sweep" else 1, mode, target, rounds, nsteps_per_round))
+        A = np.empty(self.C)
+        self._ck(self.lib.smcb_get_step_sizes(self._h, _ptr(A)))
+        return A
 
     # -- chain state -------------------------------------------------------------
     def refresh_energy(self, mode=FAST):
@@ -366,6 +391,11 @@ class Engine:
         a, b = C.c_uint64(), C.c_uint64()
         self._ck(self.lib.smcb_last_pair_counts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_pair_tests(self):
+        a = C.c_uint64()
+        self._ck(self.lib.smcb_last_pair_tests(self._h, C.byref(a)))
+        return a.value
 
     def measure_fp64_peak(self):
         t, ms = C.c_double(), C.c_float()

@@ -1,0 +1,273 @@
+"""Parity at the HEADLINE configuration and with per-element tolerances (round-2 additions).
+
+BASELINE configs[2] is N = 256 molecules, main.c geometry (L = 33, Lz = 240), T = A = 1.1.  The sweep tests of
+test_gpu_sweep.py cover that size only with A = 0.02; here the bit-exact kernel runs 1000 free sweeps and the FAST
+kernels are teacher-forced at exactly the benchmark's parameters, from the start lattice and from a thermalised gas.
+Forces are checked per ELEMENT against the conditioning of each sum, the all-particle acceptance per step from the
+oracle's state, the FAST stream's single-precision Gaussians as a distribution, and the sampler statistically at
+N = 256 with many short replica chains."""
+import numpy as np
+import pytest
+
+from smcb_helpers import (GOLDEN_W_M3, Oracle, config_droplet, expand_streams, geom, make_stream, make_sys, mixed_configs, smcb)
+
+pytestmark = pytest.mark.gpu
+N, M, T, A = 256, 3, 1.1, 1.1
+L, LZ = geom(N)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def starts(orc):
+    """the benchmark's start lattice and a gas thermalised like sMC does it (2A, SMC.c:110-125), two chains each"""
+    R0, sites = orc.initialize_box(L, LZ, N)
+    assert sites == N
+    with smcb.Engine(2, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=LZ, T=T, A=A), GOLDEN_W_M3)
+        eng.broadcast_positions(R0)
+        eng.set_rng(31337, 0, 0)
+        eng.set_step_scale(2.0)
+        eng.sweep(1500, smcb.FAST)
+        therm = eng.get_positions()
+    return {"lattice": np.stack([R0, R0]), "thermalised": therm}
+
+
+@pytest.mark.parametrize("start", ["lattice", "thermalised"])
+def test_strict_free_running_1000_sweeps_headline(orc, starts, start):
+    """north_star: "trajectories fed the same random numbers agree step-for-step": 1000 free-running sweeps at
+    N = 256, T = A = 1.1, bit for bit (positions, running energy, every accept decision)"""
+    s = make_sys(N, M, L, LZ)
+    W = GOLDEN_W_M3.copy()
+    R0 = starts[start]
+    C, total, chunk = R0.shape[0], 1000, 250
+    rng = np.random.default_rng(7 if start == "lattice" else 8)
+    Ro = [R0[c].copy() for c in range(C)]
+    with smcb.Engine(C, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=LZ, T=T, A=A), W)
+        eng.set_positions(R0)
+        eng.refresh_energy(smcb.STRICT)
+        Eo = list(eng.chain_state()[0])
+        tot = [0] * C
+        for blk in range(total // chunk):
+            streams = np.stack([make_stream(N, chunk, rng) for _ in range(C)], axis=1)
+            displ, off, u = expand_streams(orc, N, A, streams)
+            acc = eng.sweep_fed(displ, off, u, mode=smcb.STRICT, want_accepted=True)
+            R = eng.get_positions()
+            E, na, _ = eng.chain_state()
+            for c in range(C):
+                for k in range(chunk):
+                    j, Eo[c], fl = orc.sweep(s, Ro[c], W, A, T, displ[k, c], off[k, c], u[k, c], Eo[c], want_flags=True)
+                    np.testing.assert_array_equal(acc[k, c], fl, err_msg=f"accept flags, chain {c}, sweep {blk * chunk + k}")
+                    tot[c] += j
+                np.testing.assert_array_equal(R[c], Ro[c], err_msg=f"chain {c} diverged before sweep {(blk + 1) * chunk}")
+                assert E[c] == Eo[c] and na[c] == tot[c]
+    assert all(0.8 < t / (total * N) < 1.0 for t in tot)
+
+
+@pytest.mark.parametrize("start", ["lattice", "thermalised"])
+def test_fast_teacher_forced_headline(orc, starts, start):
+    """the FAST sweep kernels (the ones bench.py times) at the benchmark's parameters, re-synchronised to the oracle
+    before every sweep: identical accept decisions, positions and energy change within 1e-12"""
+    s = make_sys(N, M, L, LZ)
+    W = GOLDEN_W_M3.copy()
+    R = starts[start].copy()
+    C, nsweeps = R.shape[0], 30
+    rng = np.random.default_rng(11)
+    naccepted = 0
+    with smcb.Engine(C, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=LZ, T=T, A=A), W)
+        for k in range(nsweeps):
+            streams = np.stack([make_stream(N, 1, rng) for _ in range(C)], axis=1)
+            displ, off, u = expand_streams(orc, N, A, streams)
+            eng.set_positions(R)
+            eng.refresh_energy(smcb.FAST)
+            E0 = eng.chain_state()[0]
+            acc = eng.sweep_fed(displ, off, u, mode=smcb.FAST, want_accepted=True)
+            Rg = eng.get_positions()
+            Eg = eng.chain_state()[0]
+            for c in range(C):
+                Eo0 = orc.energy(s, R[c]) + orc.walls_energy(s, R[c], W)
+                assert abs(E0[c] - Eo0) <= 1e-12 * max(1.0, abs(Eo0))
+                j, Eo, fl = orc.sweep(s, R[c], W, A, T, displ[0, c], off[0, c], u[0, c], Eo0, want_flags=True)   # advances R[c]
+                np.testing.assert_array_equal(acc[0, c], fl, err_msg=f"sweep {k} chain {c}")
+                assert np.max(np.abs(Rg[c] - R[c]) / np.maximum(1.0, np.abs(R[c]))) < 1e-12, (k, c)
+                assert abs((Eg[c] - E0[c]) - (Eo - Eo0)) <= 1e-12 * max(1.0, abs(Eo - Eo0), abs(Eo0))
+                naccepted += j
+    assert naccepted > 0.8 * C * nsweeps * N
+
+
+def _pair_term_scale(R, Lbox):
+    """S[i, c] = sum_j |g_ij d_ij,c|: the magnitude of what is summed into force component c of molecule i - the
+    conditioning of that sum (a double-precision sum of these terms cannot be more accurate than eps * S)"""
+    X = R.reshape(-1, 3)
+    d = X[:, None, :] - X[None, :, :]
+    d[:, :, 0] -= Lbox * np.rint(d[:, :, 0] / Lbox)
+    d[:, :, 1] -= Lbox * np.rint(d[:, :, 1] / Lbox)
+    r2 = np.einsum("ijk,ijk->ij", d, d)
+    np.fill_diagonal(r2, np.inf)
+    inside = r2 < 9.0
+    r2 = np.where(inside, r2, 1.0)
+    g = np.where(inside, 48.0 / r2 ** 7 - 24.0 / r2 ** 4, 0.0)
+    return np.sum(np.abs(g)[:, :, None] * np.abs(d), axis=1)
+
+
+@pytest.mark.parametrize("n", [256, 108])
+def test_fast_forces_elementwise(orc, n):
+    """every force component of every molecule, FAST evaluation against the reference's forceSingle + wallsForce:
+    |difference| <= 1e-12 * max(|f|, S) with S the sum of the magnitudes of the terms of THAT component (so a small
+    component next to a large one is held to its own scale, not to max |f| of the configuration)"""
+    Lb, Lz = geom(n)
+    s = make_sys(n, M, Lb, Lz)
+    W = GOLDEN_W_M3.copy()
+    R = mixed_configs(n, Lb, Lz, 6, seed=123 + n, orc=orc)
+    with smcb.Engine(R.shape[0], n, M) as eng:
+        eng.set_params(smcb.default_params(L=Lb, Lz=Lz, T=T, A=A), W)
+        eng.set_positions(R)
+        ev = eng.evaluate(smcb.FAST)
+    worst = 0.0
+    for c in range(R.shape[0]):
+        f_lj = np.concatenate([orc.force_single(s, R[c], i) for i in range(n)]).reshape(n, 3)
+        f_w = np.concatenate([orc.walls_force(s, R[c][3 * i:3 * i + 3], W) for i in range(n)]).reshape(n, 3)
+        S = _pair_term_scale(R[c], Lb)
+        g_lj, g_w = ev["f_lj"][c].reshape(n, 3), ev["f_wall"][c].reshape(n, 3)
+        tol_lj = 1e-12 * np.maximum(np.abs(f_lj), S) + 1e-300
+        assert np.all(np.abs(g_lj - f_lj) <= tol_lj), (c, float(np.max(np.abs(g_lj - f_lj) / tol_lj)))
+        tol_w = 1e-12 * np.maximum(np.abs(f_w), np.abs(f_w).max(axis=1, keepdims=True)) + 1e-300     # <= 10 terms of one molecule
+        assert np.all(np.abs(g_w - f_w) <= tol_w), (c, float(np.max(np.abs(g_w - f_w) / tol_w)))
+        worst = max(worst, float(np.max(np.abs(g_lj - f_lj) / np.maximum(np.maximum(np.abs(f_lj), S), 1e-300))))
+    assert worst < 1e-12
+
+
+@pytest.mark.parametrize("mode", [smcb.FAST, smcb.STRICT])
+@pytest.mark.parametrize("n,Astep", [(256, 1e-4), (108, 2e-4), (33, 1e-3)])
+def test_allparticle_lnap_teacher_forced(orc, mode, n, Astep):
+    """the all-particle step's Metropolis-Hastings exponent, ONE step from the oracle's state at a time (no chaos
+    between the two): |ln ap - oracle| <= 1e-12 * S, S = the magnitude of what the exponent sums,
+    (|U'| + |U| + sum |d.(F'+F)|/2 + (A/4T) sum (F'^2 + F^2)) / T"""
+    Lb, Lz = geom(n)
+    s = make_sys(n, M, Lb, Lz)
+    W = GOLDEN_W_M3.copy()
+    C, nsteps = 4, 12
+    rng = np.random.default_rng(n)
+    R = mixed_configs(n, Lb, Lz, C, seed=9 * n, orc=orc)
+    nacc = 0
+    with smcb.Engine(C, n, M) as eng:
+        eng.set_params(smcb.default_params(L=Lb, Lz=Lz, T=T, A=Astep), W)
+        for k in range(nsteps):
+            xi = rng.standard_normal((1, C, 3 * n)) * np.sqrt(2 * Astep)
+            u = rng.random((1, C))
+            eng.set_positions(R)
+            lnap, acc = eng.step_allparticle_fed(xi, u, mode=mode)
+            Rg = eng.get_positions()
+            for c in range(C):
+                F, Ulj, Uw, _ = orc.total(s, R[c], W)
+                U = Ulj + Uw
+                # magnitude of the exponent's terms, from the oracle's own pieces
+                d = F * (Astep / T) + xi[0, c]
+                Rp = R[c] + d
+                Rp[0::3] -= Lb * np.rint(Rp[0::3] / Lb)
+                Rp[1::3] -= Lb * np.rint(Rp[1::3] / Lb)
+                Fp, Uljp, Uwp, _ = orc.total(s, Rp, W)
+                S = (abs(Uljp + Uwp) + abs(U) + 0.5 * np.sum(np.abs(d * (Fp + F))) + Astep / (4 * T) * np.sum(Fp * Fp + F * F)) / T
+                ok, Unew, ln = orc.allparticle_step(s, R[c], F, U, W, Astep, T, xi[0, c], u[0, c])      # advances R[c] if accepted
+                assert abs(lnap[0, c] - ln) <= 1e-12 * max(1.0, S), (k, c, lnap[0, c], ln, S)
+                assert bool(acc[0, c]) == bool(ok)
+                assert np.max(np.abs(Rg[c] - R[c]) / np.maximum(1.0, np.abs(R[c]))) < 1e-12
+                nacc += ok
+    assert nacc > 0
+
+
+def test_fast_stream_gaussians_are_standard_normal():
+    """The FAST kernels draw their displacements with a SINGLE-precision Box-Muller on Philox bits (philox.cuh): check
+    them as a distribution.  An ideal gas (cutoff 0.01, no wall, huge box) accepts every trial with probability one,
+    so positions after one sweep minus the start are exactly sqrt(2A) g: 8192 x 256 x 3 = 6.3 M samples."""
+    from scipy import stats
+    n, C, Lb = 256, 8192, 1.0e4
+    rng = np.random.default_rng(0)
+    R0 = (rng.random((n, 3)) - 0.5) * 0.5 * Lb
+    with smcb.Engine(C, n, M) as eng:
+        eng.set_params(smcb.default_params(L=Lb, Lz=Lb, T=1.0, A=0.5, rc2=1e-4, flags=0))
+        eng.broadcast_positions(R0.reshape(-1))
+        eng.set_rng(20261018, 0, 0)
+        eng.sweep(1, smcb.FAST)
+        _, na, nt = eng.chain_state()
+        g = (eng.get_positions().reshape(C, n, 3) - R0[None]).reshape(-1)        # sigma = sqrt(2A) = 1
+    assert np.all(na == nt)
+    m = g.size
+    assert abs(g.mean()) < 4.0 / np.sqrt(m)
+    assert abs(g.var() - 1.0) < 4.0 * np.sqrt(2.0 / m)
+    assert abs(stats.skew(g)) < 4.0 * np.sqrt(6.0 / m)
+    assert abs(stats.kurtosis(g)) < 4.0 * np.sqrt(24.0 / m)
+    # Kolmogorov-Smirnov on a subsample (the statistic's p-value is meaningful for independent draws)
+    sub = g[:: m // 200000]
+    assert stats.kstest(sub, "norm").pvalue > 1e-3
+    # tails: counts beyond 3, 4 and 4.5 sigma within 5 standard deviations of the Gaussian expectation
+    for z in (3.0, 4.0, 4.5):
+        expect = m * 2 * stats.norm.sf(z)
+        assert abs(np.sum(np.abs(g) > z) - expect) < 5.0 * np.sqrt(expect) + 5
+    # the three components of a molecule and neighbouring molecules are uncorrelated
+    G = g.reshape(-1, 3)
+    assert np.all(np.abs(np.corrcoef(G.T) - np.eye(3)) < 4.0 / np.sqrt(G.shape[0]))
+    assert abs(np.corrcoef(G[:-1, 0], G[1:, 0])[0, 1]) < 4.0 / np.sqrt(G.shape[0])
+
+
+def _reference_replica(c):
+    """one short replica chain of the reference's sampler (host): 150 sweeps with 2A, then 100 production sweeps"""
+    orc = Oracle()
+    s = make_sys(N, M, L, LZ)
+    W = GOLDEN_W_M3.copy()
+    R, _ = orc.initialize_box(L, LZ, N)
+    E = orc.energy(s, R) + orc.walls_energy(s, R, W)
+    _, E = orc.run_sweeps(s, R, W, 2 * A, T, 150, seed=100 + c, E=E)
+    es, acc = [], 0
+    for k in range(10):
+        a_, E = orc.run_sweeps(s, R, W, A, T, 10, seed=90000 + 31 * c + k, E=E)
+        acc += a_
+        es.append(E)
+    return np.mean(es), acc / (100 * N), R[2::3].mean()
+
+
+def test_replica_statistics_headline_geometry(orc):
+    """N = 256 in main.c's box, T = A = 1.1: many SHORT replica chains from the start lattice - 150 sweeps with 2A
+    (sMC's thermalisation) then 100 production sweeps - on the reference's sampler (128 chains on the host cores) and
+    on the FAST kernel with Philox streams (2048 chains).  Same Markov kernel => same distribution at equal time:
+    mean energy over the production window, acceptance ratio and the mean height of the gas agree within 2 sigma.
+    (Both sides are seeded, so the outcome is deterministic; 1024 further reference chains give <E> = -4.955 +- 0.020
+    against the kernel's -4.956.)"""
+    import multiprocessing as mp
+    import os
+    W = GOLDEN_W_M3.copy()
+    R0, _ = orc.initialize_box(L, LZ, N)
+    n_eq, n_prod, every = 150, 100, 10
+    with mp.get_context("fork").Pool(min(16, len(os.sched_getaffinity(0)))) as pool:
+        ref = np.array(pool.map(_reference_replica, range(1000, 1128)))
+    ref_E, ref_acc, ref_z = ref[:, 0], ref[:, 1], ref[:, 2]
+    C = 2048
+    with smcb.Engine(C, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=LZ, T=T, A=A), W)
+        eng.broadcast_positions(R0)
+        eng.set_rng(4711, 0, 0)
+        eng.set_step_scale(2.0)
+        eng.sweep(n_eq, smcb.FAST)
+        eng.set_step_scale(1.0)
+        eng.reset_counters()
+        es = []
+        for k in range(n_prod // every):
+            eng.sweep(every, smcb.FAST)
+            es.append(eng.chain_state()[0].copy())
+        _, na, nt = eng.chain_state()
+        gz = eng.get_positions().reshape(C, N, 3)[:, :, 2].mean(axis=1)
+    gE, gacc = np.mean(es, axis=0), na / nt
+
+    def close(a, b, what):
+        a, b = np.asarray(a, float), np.asarray(b, float)
+        sig = np.hypot(a.std(ddof=1) / np.sqrt(a.size), b.std(ddof=1) / np.sqrt(b.size))
+        assert abs(a.mean() - b.mean()) <= 2.0 * sig, f"{what}: reference {a.mean():.5g} vs GPU {b.mean():.5g}, 2 sigma = {2 * sig:.3g}"
+
+    close(ref_E, gE, "<E>")
+    close(ref_acc, gacc, "acceptance")
+    close(ref_z, gz, "mean height")

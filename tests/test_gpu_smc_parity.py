@@ -1,0 +1,147 @@
+"""sMC end to end (row f1, SMC.c:21-267) and its files (row f3): the drop-in's sMC on the GPU against the
+UNMODIFIED reference's sMC run here on the host (oracle/_ref, FFTW backed by the DFT shim), same arguments.
+
+The two draw different random numbers (libc rand() vs Philox), so the comparison is statistical: K independent runs
+of each, fixed seeds on both sides (the test is deterministic), means within 2 sigma of the difference.  Known
+differences of the reference that the comparison accounts for:
+  B10  after a thermalisation the reference's E[] keeps the pre-thermalisation E[0], a constant offset -> the mean
+       energy is compared for runs WITHOUT thermalisation (eqsteps = 0), cv / acceptance / P in both cases;
+  B4   the reference stores pressure sample k at P[k] (P[0] stays 0, the last one lands past the array), so its mean
+       virial part is (gs-1)/gs of the samples' mean -> rescaled before comparing.
+The CSV files the two write are compared name for name, header for header and row format for row format."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle_bindings import GOLDEN_W_M3, RAND_MAX, RefLib
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "dropin", "_build")
+N = 108
+
+
+class Sim108(ctypes.Structure):
+    _fields_ = [("E", ctypes.c_double), ("dE", ctypes.c_double), ("P", ctypes.c_double), ("dP", ctypes.c_double),
+                ("acceptance_ratio", ctypes.c_double), ("cv", ctypes.c_double), ("tau", ctypes.c_double),
+                ("Rfinal", ctypes.c_double * (3 * N)), ("l2", ctypes.c_double * 7), ("l3", ctypes.c_double * 7),
+                ("ACF_length", ctypes.c_size_t), ("ACF_data", ctypes.POINTER(ctypes.c_double))]
+
+
+def _lib(which):
+    if which == "ref":
+        lib = RefLib(N, 3)
+    else:
+        path = os.path.join(BUILD, f"libdropin_N{N}_M3.so")
+        if not os.path.exists(path):
+            pytest.fail(f"{path} missing: run `make -C tests/dropin`")
+        lib = RefLib(N, 3, path=path)
+    assert lib.lib.ref_sizeof_sim() == ctypes.sizeof(Sim108)
+    dptr = np.ctypeslib.ndpointer(dtype=np.float64)
+    lib.lib.ref_sMC.argtypes = [ctypes.c_double] * 4 + [dptr, dptr, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Sim108)]
+    return lib
+
+
+def _run(lib, workdir, maxsteps, lapse, eq, T=1.1):
+    L, Lz = 33.0, 200.0
+    cwd = os.getcwd()
+    os.makedirs(workdir, exist_ok=True)
+    os.chdir(workdir)
+    try:
+        R0 = lib.initializeBox(L, Lz)
+        sim = Sim108()
+        lib.lib.ref_sMC(L, Lz, T, T, GOLDEN_W_M3.copy(), R0, maxsteps, lapse, eq, ctypes.byref(sim))
+    finally:
+        os.chdir(cwd)
+    out = {k: getattr(sim, k) for k in ("E", "dE", "P", "dP", "acceptance_ratio", "cv", "tau")}
+    out["acf"] = np.array([sim.ACF_data[k] for k in range(sim.ACF_length)])
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+    libc.free(ctypes.cast(sim.ACF_data, ctypes.c_void_p))
+    return out
+
+
+def _many(which, tmp_path, K, maxsteps, lapse, eq, monkeypatch):
+    lib = _lib(which)
+    runs = []
+    for k in range(K):
+        if which == "ref":      # a replayed rand() stream per run (sMC's srand(time) is ignored under replay)
+            rng = np.random.default_rng(1000 + k)
+            lib.set_replay(rng.integers(0, RAND_MAX, size=(maxsteps + eq + 2) * (4 * N + 1), endpoint=True).astype(np.int32))
+        else:
+            monkeypatch.setenv("SMCB_SEED", str(5000 + k))
+            monkeypatch.setenv("SMCB_REPLICAS", "64")
+        runs.append(_run(lib, tmp_path / f"{which}_{eq}_{k}", maxsteps, lapse, eq))
+        if which == "ref":
+            assert lib.replay_underflow() == 0
+            lib.set_replay(None)
+    return runs
+
+
+def _within_2_sigma(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    d = abs(a.mean() - b.mean())
+    s = np.sqrt(a.var(ddof=1) / a.size + b.var(ddof=1) / b.size)
+    assert d <= 2.0 * s + 1e-12 * max(1.0, abs(a.mean())), f"{what}: reference {a.mean():.6g} vs drop-in {b.mean():.6g}, |diff| {d:.3g} > 2 sigma = {2 * s:.3g}"
+
+
+@pytest.mark.parametrize("eq", [0, 100])
+def test_sMC_observables_within_2_sigma_of_the_reference(tmp_path, monkeypatch, eq):
+    maxsteps, lapse, K = 400, 20, 12
+    gs = maxsteps // lapse
+    ref = _many("ref", tmp_path, K, maxsteps, lapse, eq, monkeypatch)
+    got = _many("dropin", tmp_path, K, maxsteps, lapse, eq, monkeypatch)
+    rhoT = N / (33.0 * 33.0 * 200.0) * 1.1
+    _within_2_sigma([r["acceptance_ratio"] for r in ref], [r["acceptance_ratio"] for r in got], "acceptance_ratio")
+    _within_2_sigma([r["cv"] for r in ref], [r["cv"] for r in got], "cv")
+    _within_2_sigma([(r["P"] - rhoT) * gs / (gs - 1) for r in ref], [r["P"] - rhoT for r in got], "P (virial part, B4 rescaled)")
+    if eq == 0:
+        _within_2_sigma([r["E"] for r in ref], [r["E"] for r in got], "E")
+        _within_2_sigma([r["dE"] for r in ref], [r["dE"] for r in got], "dE")
+    for r in ref + got:
+        assert r["acf"].size == maxsteps // 2 - 2 and abs(r["acf"][0] - 1.0) < 1e-12          # k_max reduced as the reference does
+        assert abs(r["tau"] - r["acf"].sum()) < 1e-9 * max(1.0, abs(r["tau"]))               # tau = sum(acf), SMC.c:238-240
+
+
+ROW = {
+    "data": r"^-?\d+\.\d{9}, -?\d+\.\d{9}, \d+$",
+    "local": r"^\d+, \d+, \d+, \d+, \d+$",
+    "local_temp": r"^\d+, \d+, \d+, \d+, \d+$",
+    "total_clusters": r"^-?(\d+\.\d{9}|nan|inf), -?(\d+\.\d{9}|nan|inf), -?(\d+\.\d{9}|nan|inf)$",
+    "autocorrelation": r"^-?\d+\.\d{6}$",
+}
+
+
+def test_sMC_csv_files_have_the_reference_format(tmp_path, monkeypatch):
+    """same file names, byte-identical headers and first lines that do not depend on the random stream (the positions
+    header and the start configuration), same number of rows, every row in the reference's printf format"""
+    maxsteps, lapse, eq = 200, 10, 20
+    _many("ref", tmp_path, 1, maxsteps, lapse, eq, monkeypatch)
+    monkeypatch.setenv("SMCB_REPLICAS", "1")
+    lib = _lib("dropin")
+    monkeypatch.setenv("SMCB_SEED", "9")
+    _run(lib, tmp_path / "drop", maxsteps, lapse, eq)
+    rdir, ddir = tmp_path / f"ref_{eq}_0", tmp_path / "drop"
+    rnames, dnames = sorted(p.name for p in rdir.iterdir()), sorted(p.name for p in ddir.iterdir())
+    assert rnames == dnames and len(rnames) == 6
+    for name in rnames:
+        kind = name.split("_N108")[0]
+        rl, dl = (rdir / name).read_text().split("\n"), (ddir / name).read_text().split("\n")
+        assert rl[0] == dl[0], f"{name}: header {dl[0]!r} != reference {rl[0]!r}"
+        if kind == "positions":
+            assert rl[1] == dl[1]                         # R0 in %0.3lf
+            continue
+        assert len(rl) == len(dl), f"{name}: {len(dl)} lines vs reference {len(rl)}"
+        pat = re.compile(ROW[kind])
+        for line in rl[1:-1]:
+            assert pat.match(line), f"reference {name}: {line!r} does not match the expected format (test is wrong)"
+        for line in dl[1:-1]:
+            assert pat.match(line), f"{name}: {line!r} is not in the reference's row format"
+        assert rl[-1] == dl[-1] == ""
+        if kind in ("local", "local_temp"):                # same voxel order
+            assert [l.split(", ")[:3] for l in rl[1:50]] == [l.split(", ")[:3] for l in dl[1:50]]
+            if kind == "local":
+                assert sum(int(l.split(", ")[3]) for l in dl[1:-1]) == sum(int(l.split(", ")[3]) for l in rl[1:-1]) == N * (maxsteps // lapse)
