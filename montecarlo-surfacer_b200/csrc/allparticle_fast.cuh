@@ -250,7 +250,7 @@ __device__ __forceinline__ void allparticle_fast_body(const DevChains &d, const 
     s.carve(sm, Npad, N, HALF);
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, d.step_scale);
-    const ScreenConsts sc = make_screen(b);
+    const ScreenConsts sc = make_screen(b, d.extent ? d.extent + 2 * chain : nullptr);
     const double *W = d.W + (size_t)cp.wall * 2 * d.M * d.M;
     double *P = d.pos + (size_t)chain * 3 * Npad;
     double *Fc = a.F + (size_t)chain * 3 * Npad;
@@ -453,7 +453,7 @@ __device__ __forceinline__ void evaluate_fast_body(const DevChains &d, const Eva
     __shared__ unsigned s_last;
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, 1.0);
-    const ScreenConsts sc = make_screen(b);
+    const ScreenConsts sc = make_screen(b, d.extent ? d.extent + 2 * chain : nullptr);
     const double *W = d.W + (size_t)cp.wall * 2 * d.M * d.M;
     const double *P = d.pos + (size_t)chain * 3 * Npad;
     // the chain's [3][Npad] position block -> s.x/s.y/s.z in one bulk-async copy (pad slots hold 0 in HBM)

@@ -79,7 +79,9 @@ struct smcb_engine {
     DevBuf<long long> nacc, ntri, fed_off;
     DevBuf<unsigned long long> pairs, counters;
     DevBuf<unsigned char> fed_acc;
-    DevBuf<int> rbin, trace_acc;
+    DevBuf<int> rbin, trace_acc, extent_flag;
+    DevBuf<float> extent;                   // [C][2] box-unit extent of every chain at upload (FP32 screen bound)
+    int *flag_pinned = nullptr;
     DevBuf<double> eval_partials, chain_mom;
     DevBuf<unsigned> eval_tickets;
     DevBuf<double> trace_E;
@@ -100,6 +102,7 @@ struct smcb_engine {
         d.C = C; d.N = N; d.Npad = Npad; d.M = M;
         d.params = params.p; d.nparams = nparams; d.W = W.p; d.pos = pos.p; d.E = E.p;
         d.nacc = nacc.p; d.ntri = ntri.p; d.step_scale = step_scale; d.pair_counts = pairs.p;
+        d.extent = extent.p;
         return d;
     }
     size_t u64_per_group() const { return (size_t)2 * SMCB_NCX * SMCB_NCX * SMCB_NCZ + SMCB_NCZ + nebins + 1; }
@@ -120,6 +123,23 @@ static int need_ready(smcb_engine *e)
     if (rc) return rc;
     if (!e->have_params) return fail(SMCB_ERR_STATE, "smcb_set_params has not been called");
     if (!e->have_pos) return fail(SMCB_ERR_STATE, "smcb_set_positions has not been called");
+    return SMCB_OK;
+}
+
+// After new positions reach the device: every chain's extent in box units (the FAST kernels' FP32 screen derives its
+// error bound from it) and a check that the coordinates can be screened in single precision at all.
+static int positions_uploaded(smcb_engine *e)
+{
+    if (!e->have_params) return SMCB_OK;                 // extents need L: computed when the parameters arrive
+    CK(launch_chain_extent(e->chains(), e->extent.p, e->extent_flag.p, e->stream));
+    CK(cudaMemcpyAsync(e->flag_pinned, e->extent_flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (*e->flag_pinned) {
+        CK(cudaMemsetAsync(e->extent_flag.p, 0, sizeof(int), e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->have_pos = false;
+        return fail(SMCB_ERR_ARG, "positions contain NaN or coordinates more than 2^20 box lengths from the origin");
+    }
     return SMCB_OK;
 }
 
@@ -173,6 +193,10 @@ int smcb_create(smcb_engine **out, int device, int nchains, int N, int M)
         if (a == cudaSuccess) a = cudaEventCreateWithFlags(&e->pev[p], cudaEventDisableTiming);
     }
     if (a == cudaSuccess) a = cudaMallocHost(&e->pairs_pinned, 3 * sizeof(unsigned long long));
+    if (a == cudaSuccess) a = cudaMallocHost(&e->flag_pinned, sizeof(int));
+    if (a == cudaSuccess) a = e->extent.ensure((size_t)2 * nchains);
+    if (a == cudaSuccess) a = e->extent_flag.ensure(1);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->extent_flag.p, 0, sizeof(int), e->stream);
     if (a == cudaSuccess) a = e->pos.ensure(3 * cn);
     if (a == cudaSuccess) a = e->E.ensure(nchains);
     if (a == cudaSuccess) a = e->nacc.ensure(nchains);
@@ -211,6 +235,8 @@ int smcb_destroy(smcb_engine *e)
     }
     if (e->pstart) cudaEventDestroy(e->pstart);
     if (e->pairs_pinned) cudaFreeHost(e->pairs_pinned);
+    if (e->flag_pinned) cudaFreeHost(e->flag_pinned);
+    e->extent.release(); e->extent_flag.release();
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -282,7 +308,8 @@ int smcb_set_params(smcb_engine *e, const smcb_chain_params *p, int nparams, con
     e->have_params = true; e->energy_valid = false; e->forces_valid = false;
     e->params_hash = fnv1a(p, (size_t)nparams * sizeof(*p));
     if (W && nwalls > 0) e->params_hash = fnv1a(W, wlen * sizeof(double), e->params_hash);
-    return obs_alloc(e, true);
+    if ((rc = obs_alloc(e, true))) return rc;
+    return e->have_pos ? positions_uploaded(e) : SMCB_OK;      // L may have changed: extents are in box units
 }
 
 int smcb_set_positions(smcb_engine *e, const double *R)
@@ -296,7 +323,7 @@ int smcb_set_positions(smcb_engine *e, const double *R)
     CK(launch_aos_to_soa(e->stage.p, e->pos.p, e->C, e->N, e->Npad, 3, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->have_pos = true; e->energy_valid = false; e->forces_valid = false;
-    return SMCB_OK;
+    return positions_uploaded(e);
 }
 
 int smcb_broadcast_positions(smcb_engine *e, const double *R0)
@@ -316,7 +343,7 @@ int smcb_broadcast_positions(smcb_engine *e, const double *R0)
     CK(launch_aos_to_soa(e->stage.p, e->pos.p, e->C, e->N, e->Npad, 3, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->have_pos = true; e->energy_valid = false; e->forces_valid = false;
-    return SMCB_OK;
+    return positions_uploaded(e);
 }
 
 int smcb_get_positions(smcb_engine *e, double *R)
@@ -579,6 +606,7 @@ static DevChains sub_chains(smcb_engine *e, int c0, int cn)
     d.C = cn;
     d.pos += (size_t)c0 * 3 * e->Npad;
     d.E += c0; d.nacc += c0; d.ntri += c0;
+    d.extent += (size_t)2 * c0;
     if (d.nparams != 1) d.params += c0;
     return d;
 }
@@ -638,6 +666,7 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
         // in: positions; E <- energy + wallsEnergy of them (SMC.c:48) comes out of the kernel's own cache rebuild
         CK(cudaMemcpyAsync(e->stage.p + aoff, R + aoff, an * sizeof(double), cudaMemcpyHostToDevice, st));
         CK(launch_aos_to_soa(e->stage.p + aoff, d.pos, cn, N, Npad, 3, st));
+        CK(launch_chain_extent(d, e->extent.p + (size_t)2 * c0, e->extent_flag.p, st));
         if (!kernel_refreshes) {             // STRICT / block-per-chain sweeps read d.E: evaluate it first
             EvalOut o{};
             o.totals = e->totals.p + (size_t)c0 * kTot;
@@ -682,8 +711,15 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
     }
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaMemcpyAsync(e->pairs_pinned, e->pairs.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->flag_pinned, e->extent_flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    if (*e->flag_pinned) {
+        CK(cudaMemsetAsync(e->extent_flag.p, 0, sizeof(int), e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->have_pos = false;
+        return fail(SMCB_ERR_ARG, "positions contain NaN or coordinates more than 2^20 box lengths from the origin");
+    }
     for (int k = 0; k < 3; k++) e->last_pairs[k] = e->pairs_pinned[k];
     e->last_launches = parts * 3 + (gather ? 3 : 0);
     if (kernel == 0 && mode == SMCB_FAST) e->sweep_dense = e->last_pairs[1] * 50ull > e->last_pairs[0] ? 1 : 0;
@@ -1127,7 +1163,7 @@ int smcb_checkpoint_load(smcb_engine *e, const char *path)
     e->seed = h.seed; e->chain0 = h.chain0; e->step = h.step; e->step_scale = h.step_scale;
     e->sweep_dense = h.pad_ == 1u ? 1 : 0;      // the resumed run launches the kernel the saved run would have launched next
     e->have_pos = true; e->energy_valid = true; e->forces_valid = false;
-    return SMCB_OK;
+    return positions_uploaded(e);
 }
 
 // -------------------------------------------------------------- measurement

@@ -30,6 +30,7 @@ struct DevChains {
     double *E;                // [C] running potential energy
     long long *nacc, *ntri;   // [C]
     double step_scale;        // A multiplier (thermalisation uses 2, SMC.c:110)
+    const float *extent;      // nullable [C][2]: max |x|/L,|y|/L and max |z|/L of the chain at upload (FP32 screen bound)
     unsigned long long *pair_counts;   // [0] ordered pair-interactions as the reference executes them (nominal), [1] of them inside
                                        // the cutoff, [2] pair distance tests the kernel actually EXECUTED (cached / screened / half-shell
                                        // kernels execute fewer than [0])
@@ -702,6 +703,31 @@ __global__ void k_energy_from_totals(const double *__restrict__ totals, double *
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) E[c] = totals[(size_t)c * kTot] + totals[(size_t)c * kTot + 1];
+}
+
+// Extent of every chain's configuration in box units, for the FP32 screen's error bound (make_screen): one warp per
+// chain.  Coordinates beyond 2^20 boxes (or NaN) cannot be screened in single precision at all: flagged.
+__global__ void k_chain_extent(const double *__restrict__ pos, const smcb_chain_params *__restrict__ params, int nparams,
+                               int C, int N, int Npad, float *__restrict__ extent, int *__restrict__ flag)
+{
+    const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (chain >= C) return;
+    const double invL = 1.0 / params[nparams == 1 ? 0 : chain].L;
+    const double *P = pos + (size_t)chain * 3 * Npad;
+    float axy = 0.f, az = 0.f;
+    bool bad = false;
+    for (int j = lane; j < N; j += 32) {
+        const double x = fabs(P[j]) * invL, y = fabs(P[Npad + j]) * invL, z = fabs(P[2 * Npad + j]) * invL;
+        bad |= !(x < 1048576.0) || !(y < 1048576.0) || !(z < 1048576.0);
+        axy = fmaxf(axy, (float)fmax(x, y));
+        az = fmaxf(az, (float)z);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        axy = fmaxf(axy, __shfl_xor_sync(FULL, axy, o));
+        az = fmaxf(az, __shfl_xor_sync(FULL, az, o));
+    }
+    if (__any_sync(FULL, bad) && lane == 0) atomicOr(flag, 1);
+    if (lane == 0) { extent[2 * chain] = axy * 1.0000002f; extent[2 * chain + 1] = az * 1.0000002f; }   // round up
 }
 
 // step-size control (pre-production only): A[c] *= exp(gain * (acceptance[c] - target)), counters cleared

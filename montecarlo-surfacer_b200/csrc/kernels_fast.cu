@@ -52,6 +52,12 @@ cudaError_t launch_gather_moments(const DevChains &d, const GatherArgs &g, cudaS
     return cudaGetLastError();
 }
 
+cudaError_t launch_chain_extent(const DevChains &d, float *extent, int *flag, cudaStream_t st)
+{
+    k_chain_extent<<<(d.C + 7) / 8, 256, 0, st>>>(d.pos, d.params, d.nparams, d.C, d.N, d.Npad, extent, flag);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_adapt_step(smcb_chain_params *params, long long *nacc, long long *ntri, int C, double target, double gain,
                               double a_min, double a_max, cudaStream_t st)
 {

@@ -19,6 +19,7 @@ cudaError_t launch_evaluate_fast_screened(const DevChains &d, const EvalOut &o, 
 cudaError_t launch_gather(const DevChains &d, const GatherArgs &g, cudaStream_t st);
 cudaError_t launch_gather_chains(const DevChains &d, const GatherArgs &g, cudaStream_t st);
 cudaError_t launch_gather_moments(const DevChains &d, const GatherArgs &g, cudaStream_t st);
+cudaError_t launch_chain_extent(const DevChains &d, float *extent, int *flag, cudaStream_t st);
 cudaError_t launch_adapt_step(smcb_chain_params *params, long long *nacc, long long *ntri, int C, double target, double gain,
                               double a_min, double a_max, cudaStream_t st);
 cudaError_t launch_energy_from_totals(const double *totals, double *E, int C, cudaStream_t st);

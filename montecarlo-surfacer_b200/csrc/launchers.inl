@@ -85,6 +85,9 @@ static cudaError_t sweep_block_launch(bool fed, const DevChains &d, const SweepA
 {
     int threads = 256;
     if (const char *env = getenv("SMCB_BLOCK_SWEEP_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 512 && v % 32 == 0) threads = v; }
+    // a thread keeps two hit bits per screen iteration in one 32-bit word: at most 16 iterations (block_eval_point)
+    while ((d.Npad / 2 + threads - 1) / threads > 16 && threads < 512) threads += 32;
+    if ((d.Npad / 2 + threads - 1) / threads > 16) return cudaErrorInvalidValue;
     const size_t smem = BlockSweepSmem::bytes(d.Npad, threads);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t err;

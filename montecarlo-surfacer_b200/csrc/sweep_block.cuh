@@ -127,7 +127,7 @@ __device__ __forceinline__ void sweep_block_body(const DevChains &d, const Sweep
     s.carve(sm, Npad, T_);
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, d.step_scale);
-    const ScreenConsts sc = make_screen(b);
+    const ScreenConsts sc = make_screen(b, d.extent ? d.extent + 2 * chain : nullptr);
     const double *W = d.W + (size_t)cp.wall * 2 * d.M * d.M;
     double *P = d.pos + (size_t)chain * 3 * Npad;
     for (int j = tid; j < Npad; j += T_) {

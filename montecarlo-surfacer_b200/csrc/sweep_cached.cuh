@@ -65,14 +65,18 @@ struct ScreenConsts {
     float zper, inv_zper;     // Lz/L and L/Lz (bulk mode only)
 };
 
-// FP32 error bound of a box-unit separation: operands are rounded to float (|x|,|y| <= 1/2, |z| <= Lz/L
-// allowing excursions), differences and the wrap add one more rounding each.  Four times that bound is
-// added to the cutoff RADIUS, so a pair inside the true cutoff can never be screened out.
-__device__ __forceinline__ ScreenConsts make_screen(const Box &b)
+// FP32 error bound of a box-unit separation: operands are rounded to float, differences and the wrap add one more
+// rounding each.  Four times that bound is added to the cutoff RADIUS, so a pair inside the true cutoff can never be
+// screened out.  The operands' magnitude comes from the chain's EXTENT - the largest |x|/L, |y|/L and |z|/L the engine
+// found when the positions were uploaded (k_chain_extent): callers may hand over configurations that are not wrapped
+// into the primary cell (the reference tolerates that too, it only wraps the molecule it moves, SMC.c:315-316).
+// Moves wrap x,y into [-L/2, L/2] and the walls bound z, so the extent at upload bounds every later position.
+__device__ __forceinline__ ScreenConsts make_screen(const Box &b, const float *extent = nullptr)
 {
     const double eps = 1.1920929e-7;                       // 2^-23
-    const double zmax = b.Lz * b.invL + 1.0;
-    const double delta = eps * (2.0 + 2.0 * zmax);
+    const double axy = fmax(0.5, extent ? (double)extent[0] : 0.5);
+    const double zmax = fmax(b.Lz * b.invL + 1.0, extent ? (double)extent[1] : 0.0);
+    const double delta = eps * (4.0 * axy + 2.0 * zmax);
     const double rcs = sqrt(b.rc2) * b.invL + 4.0 * delta;
     ScreenConsts sc;
     sc.rc2s = (float)(rcs * rcs * (1.0 + 1e-6));
@@ -299,7 +303,7 @@ __device__ __forceinline__ void sweep_cached_body(const DevChains &d, const Swee
         }
     }
     __syncwarp();
-    const ScreenConsts sc = make_screen(b);
+    const ScreenConsts sc = make_screen(b, d.extent ? d.extent + 2 * chain : nullptr);
 
     // ---- rebuild the caches from the positions ------------------------------------
     double Erebuilt = 0.0;

@@ -85,7 +85,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
         }
     }
     __syncwarp();
-    const ScreenConsts sc = make_screen(b);
+    const ScreenConsts sc = make_screen(b, d.extent ? d.extent + 2 * chain : nullptr);
 
     // ---- rebuild the caches from the positions ------------------------------------
     double Erebuilt = 0.0;

@@ -170,3 +170,65 @@ def test_checkpoint_guards(tmp_path):
             eng.checkpoint_load(tmp_path / "bins.smcb")
         eng.checkpoint_load(ck)
         np.testing.assert_array_equal(eng.get_positions(), Rsaved)
+
+
+@pytest.mark.parametrize("shift", [1, 7, 1000])
+def test_fast_kernels_accept_unwrapped_positions(shift):
+    """the reference tolerates configurations that are not wrapped into the primary cell (it only wraps the
+    molecule it moves, SMC.c:315-316).  The FAST kernels' single-precision screen must still find every pair inside
+    the cutoff when molecules are given several box images away: its error bound follows the chain's extent.
+    FAST against STRICT (no screen) on the same shifted configuration, then a FAST sweep whose caches and partner
+    counts must equal a fresh STRICT evaluation."""
+    N, C = 108, 6
+    L, Lz = geom(N)
+    rng = np.random.default_rng(shift)
+    R = np.stack([config_droplet(N, L, Lz, rng, jitter=0.05, nz=4) for _ in range(C)]).reshape(C, N, 3)
+    k = rng.integers(-shift, shift + 1, size=(C, N, 2))
+    R[:, :, :2] += L * k                                            # whole box images: the physics is unchanged
+    R = R.reshape(C, -1)
+    with smcb.Engine(C, N, 3) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=1.1, A=0.02), GOLDEN_W_M3)
+        eng.set_positions(R)
+        fast, strict = eng.evaluate(smcb.FAST), eng.evaluate(smcb.STRICT)
+        for key in ("e_lj", "f_lj", "e_wall", "f_wall"):
+            scale = np.maximum(np.abs(strict[key]), np.abs(strict[key]).max() * 1e-6 + 1e-300)
+            assert np.all(np.abs(fast[key] - strict[key]) <= 1e-9 * scale), key      # 1e-9: the shift itself costs digits of x
+        assert np.all(np.abs(fast["U_lj"] - strict["U_lj"]) <= 1e-9 * np.abs(strict["U_lj"]))
+        eng.set_rng(5, 0, 0)
+        eng.debug_capture_cache(True)
+        eng.sweep(5, smcb.FAST)
+        ce, cf, nb = eng.debug_get_cache()
+        Rn = eng.get_positions()
+        E, na, _ = eng.chain_state()
+        ev = eng.evaluate(smcb.STRICT)
+    assert na.sum() > 0
+    for c in range(C):
+        X = Rn[c].reshape(N, 3)
+        d = X[:, None, :] - X[None, :, :]
+        d[:, :, :2] -= L * np.rint(d[:, :, :2] / L)
+        r2 = np.einsum("ijk,ijk->ij", d, d)
+        np.fill_diagonal(r2, 1e30)
+        if not (np.abs(r2 - 9.0) < 1e-6).any():
+            np.testing.assert_array_equal(nb[c], (r2 < 9.0).sum(axis=1))
+        etot = ev["e_lj"][c] + ev["e_wall"][c]
+        assert np.all(np.abs(ce[c] - etot) <= 1e-8 * np.maximum(np.abs(etot), np.abs(etot).max() * 1e-3))
+    Erec = ev["U_lj"] + ev["U_wall"]
+    assert np.all(np.abs(E - Erec) <= 1e-8 * np.maximum(1.0, np.abs(Erec)))
+
+
+def test_positions_that_cannot_be_screened_are_refused():
+    N, C = 32, 2
+    L, Lz = geom(N)
+    R, _, _ = _start(N, C)
+    with smcb.Engine(C, N, 3) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz), GOLDEN_W_M3)
+        bad = R.copy()
+        bad[1, 5] = np.nan
+        with pytest.raises(smcb.SmcbError, match="NaN or coordinates"):
+            eng.set_positions(bad)
+        bad = R.copy()
+        bad[0, 3] += 3.0e6 * L
+        with pytest.raises(smcb.SmcbError, match="NaN or coordinates"):
+            eng.set_positions(bad)
+        eng.set_positions(R)                         # the engine is usable afterwards
+        eng.sweep(1, smcb.FAST)
