@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--impl", default="smcb200", choices=["smcb200", "reference"])
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default 8192; largeN: 256/world)")
     ap.add_argument("--sweeps-per-step", type=int, default=40)
-    ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict", "fp32"],
+                    help="fast / strict: FP64 arithmetic (fast = the headline); fp32: the optional single-precision mode "
+                         "(all-particle kernel only; its own line, \"dtype\": \"f32\", never the headline)")
     ap.add_argument("--kernel", default="sweep", choices=["sweep", "allparticle"])
     ap.add_argument("--workload", default="batched", choices=["batched", "bulk", "grid", "largeN"],
                     help="batched: 8192 chains x N=256 per GPU (configs[2], the headline); grid: 65536 chains in total on a "
@@ -311,7 +313,9 @@ def main():
         lzs = [120.0, 160.0, 200.0, 240.0]
         walls = [0, 1, 2, 3]                         # wall tables: ymin = 2.0, 2.67, 3.33, 4.0 (main.c:76 uses 3.0 +- 0.5)
         grid = (shard, temps, lzs, walls, total_grid)
-    mode = smcb.STRICT if args.mode == "strict" else smcb.FAST
+    mode = smcb.STRICT if args.mode == "strict" else (smcb.FP32 if args.mode == "fp32" else smcb.FAST)
+    if mode == smcb.FP32:
+        args.kernel = "allparticle"
     A = TEMP if args.kernel == "sweep" else (2e-4 if N <= 256 else 2e-6)
     if args.start == "droplet" and args.kernel == "sweep":
         A = 0.02                                     # A = T moves 1.5 sigma per trial: nothing is accepted inside a liquid
@@ -470,7 +474,18 @@ def main():
         host_na = torch.empty(Cn, dtype=torch.int64).pin_memory().numpy()
         host_nt = torch.empty(Cn, dtype=torch.int64).pin_memory().numpy()
 
+        def e2e_step_separate():
+            # SMCB_FP32 is not offered by the pipelined call: the same step through the individual entry points
+            eng.set_positions(host_R)
+            run_kernel(args.kernel)
+            eng.gather()
+            allreduce_obs()
+            eng.get_positions(host_R)
+            return eng.chain_state()
+
         def e2e_step():
+            if mode == smcb.FP32:
+                return e2e_step_separate()
             # ONE C-ABI call with host buffers: H2D of the step's positions, energy refresh, S sweeps, gather, D2H of the new
             # positions and the chain state; inside, four chain blocks on four streams overlap their copies and kernels
             eng.sweep_host(host_R, S, mode, kernel=args.kernel, gather=True, E=host_E, naccept=host_na, ntrials=host_nt)
@@ -557,7 +572,7 @@ def main():
             "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": ("strong" if strong_batched else "weak") if args.workload in ("batched", "bulk") else ("weak" if (grid and args.chains) else "strong"),
             "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32" if mode == smcb.FP32 else "f64", "data": "synthetic",
             "config": {"workload": (f"{Cn} chains/GPU x N={N} with wall (BASELINE configs[2])" if args.workload == "batched"
                                     else f"{Cn} chains/GPU x N={N} bulk, 3-D periodic, rho*=0.5, T*=1.0 (BASELINE configs[0] geometry)" if bulk
                                     else f"{grid[4]} chains x N={N} on a 16 T x 4 Lz x 4 wall grid x replicas (BASELINE configs[3]), "

@@ -47,6 +47,11 @@ extern "C" {
                            cutoff is evaluated in FP64 (same sums as an all-FP64 loop); <= 1e-12 rel.  */
 #define SMCB_STRICT  1  /* the reference's IEEE operation order (no FMA, true divisions, sums in
                            the reference's particle order): bit-identical per-particle results   */
+#define SMCB_FP32    2  /* optional single precision: smcb_evaluate, smcb_refresh_energy and smcb_step_allparticle(_fed)
+                           only.  Coordinates are carried as float pairs (hi + lo), all pair arithmetic is FP32,
+                           block sums FP64; energies and forces within 1e-5 of the reference's (relative to the
+                           magnitude of what each sum adds up).  Molecules must be between the walls: the reference's
+                           clamp for escaped ones (SMC.c:738-739) gives r^-12 = 1e48, beyond a float.              */
 
 /* voxel grid of localDensityAndMobility (SMC.h:50-53: Ncx = Ncz = 33) */
 #define SMCB_NCX 33

@@ -6,13 +6,13 @@ view of that ABI used by tests/, bench.py and Python drivers.  It never falls ba
 implementation: importing works without a GPU (so the C-ABI export check can run), creating an
 Engine does not.
 """
-from .engine import (FAST, STRICT, WALL, PERIODIC_Z, ChainParams, Engine, ObsLayout, SmcbError,
+from .engine import (FAST, STRICT, FP32, WALL, PERIODIC_Z, ChainParams, Engine, ObsLayout, SmcbError,
                      default_params, lib_path, load_library, exported_symbols, header_symbols,
                      obs_layout_host, unpack_obs, obs_allreduce, REFERENCE_WALL_M3)
 from .shard import (Shard, shard_chains, grid_points, grid_chain_params, allreduce_observables,
                     max_over_ranks)
 
-__all__ = ["FAST", "STRICT", "WALL", "PERIODIC_Z", "ChainParams", "Engine", "ObsLayout", "SmcbError",
+__all__ = ["FAST", "STRICT", "FP32", "WALL", "PERIODIC_Z", "ChainParams", "Engine", "ObsLayout", "SmcbError",
            "default_params", "lib_path", "load_library", "exported_symbols", "header_symbols",
            "obs_layout_host", "unpack_obs", "obs_allreduce", "REFERENCE_WALL_M3", "Shard", "shard_chains", "grid_points", "grid_chain_params",
            "allreduce_observables", "max_over_ranks"]

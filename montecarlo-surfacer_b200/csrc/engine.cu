@@ -387,6 +387,10 @@ static int run_evaluate(smcb_engine *e, int mode, const EvalOut &o)
         CK(launch_evaluate_strict(d, o, e->stream));
         return SMCB_OK;
     }
+    if (mode == SMCB_FP32) {
+        CK(launch_evaluate_f32(d, o, e->stream));
+        return SMCB_OK;
+    }
     // FAST: packed-FP32 screened pair loop, several blocks per chain when the batch is small
     const int parts = evaluate_fast_parts(d);
     CK(e->eval_partials.ensure((size_t)e->C * parts * kTot));
@@ -413,7 +417,7 @@ int smcb_evaluate(smcb_engine *e, int mode, double *e_lj, double *f_lj, double *
 {
     int rc = need_ready(e);
     if (rc) return rc;
-    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
+    if (mode != SMCB_FAST && mode != SMCB_STRICT && mode != SMCB_FP32) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
     const size_t cn = (size_t)e->C * e->Npad;
     EvalOut o{};
     if (e_lj) { CK(e->e_lj.ensure(cn)); o.e_lj = e->e_lj.p; }
@@ -463,6 +467,7 @@ int smcb_refresh_energy(smcb_engine *e, int mode)
 {
     int rc = need_ready(e);
     if (rc) return rc;
+    if (mode != SMCB_FAST && mode != SMCB_STRICT && mode != SMCB_FP32) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
     return refresh_energy(e, mode);
 }
 
@@ -516,6 +521,7 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
     int rc = need_ready(e);
     if (rc) return rc;
     if (nsweeps < 0) return fail(SMCB_ERR_ARG, "nsweeps < 0");
+    if (mode == SMCB_FP32) return fail(SMCB_ERR_ARG, "SMCB_FP32 covers the static evaluation and the all-particle step; the sweep runs in SMCB_FAST or SMCB_STRICT");
     if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
     if (e->N > kSweepMaxN && mode == SMCB_STRICT)
         return fail(SMCB_ERR_ARG, "the STRICT (bit-exact) sweep kernel supports N <= %d (N = %d): use SMCB_FAST", kSweepMaxN, e->N);
@@ -619,7 +625,7 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
     if (!e->have_params) return fail(SMCB_ERR_STATE, "smcb_set_params has not been called");
     if (!R) return fail(SMCB_ERR_ARG, "R is null");
     if (nsteps <= 0) return fail(SMCB_ERR_ARG, "nsteps must be positive");
-    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
+    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "smcb_sweep_host runs in SMCB_FAST or SMCB_STRICT (got mode %d)", mode);
     if (kernel != 0 && kernel != 1) return fail(SMCB_ERR_ARG, "kernel: 0 = sweep (oneParticleMoves), 1 = all-particle step");
     if (kernel == 0 && e->N > kSweepMaxN && mode == SMCB_STRICT)
         return fail(SMCB_ERR_ARG, "the STRICT (bit-exact) sweep kernel supports N <= %d (N = %d): use SMCB_FAST", kSweepMaxN, e->N);
@@ -737,7 +743,7 @@ static int step_common(smcb_engine *e, int nsteps, int mode, bool fed, const dou
     int rc = need_ready(e);
     if (rc) return rc;
     if (nsteps < 0) return fail(SMCB_ERR_ARG, "nsteps < 0");
-    if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
+    if (mode != SMCB_FAST && mode != SMCB_STRICT && mode != SMCB_FP32) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
     if ((size_t)(6 * e->Npad + 256) * sizeof(double) > 227 * 1024)
         return fail(SMCB_ERR_ARG, "N = %d does not fit one CTA's shared memory", e->N);
     if (nsteps == 0) return SMCB_OK;
@@ -762,13 +768,15 @@ static int step_common(smcb_engine *e, int nsteps, int mode, bool fed, const dou
     CK(cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     const DevChains d = e->chains();
-    CK(mode == SMCB_STRICT ? launch_allparticle_strict(fed, d, a, e->stream) : launch_allparticle_fast(fed, d, a, e->stream));
+    CK(mode == SMCB_STRICT ? launch_allparticle_strict(fed, d, a, e->stream)
+                           : (mode == SMCB_FP32 ? launch_allparticle_f32(fed, d, a, e->stream) : launch_allparticle_fast(fed, d, a, e->stream)));
     if ((rc = finish_timed(e, 1))) return rc;
     if (lnap) CK(cudaMemcpyAsync(lnap, a.lnap, sc * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (accepted) CK(cudaMemcpyAsync(accepted, a.accepted, sc, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (!fed) e->step += (uint64_t)nsteps;
-    e->forces_valid = true; e->energy_valid = true;
+    e->forces_valid = mode != SMCB_FP32;        // the FP32 step leaves float images in the force buffers
+    e->energy_valid = true;
     return SMCB_OK;
 }
 

@@ -16,6 +16,8 @@ cudaError_t launch_evaluate_strict(const DevChains &d, const EvalOut &o, cudaStr
 
 int evaluate_fast_parts(const DevChains &d);
 cudaError_t launch_evaluate_fast_screened(const DevChains &d, const EvalOut &o, int parts, double *partials, unsigned *tickets, cudaStream_t st);
+cudaError_t launch_evaluate_f32(const DevChains &d, const EvalOut &o, cudaStream_t st);
+cudaError_t launch_allparticle_f32(bool fed, const DevChains &d, const StepArgs &a, cudaStream_t st);
 cudaError_t launch_gather(const DevChains &d, const GatherArgs &g, cudaStream_t st);
 cudaError_t launch_gather_chains(const DevChains &d, const GatherArgs &g, cudaStream_t st);
 cudaError_t launch_gather_moments(const DevChains &d, const GatherArgs &g, cudaStream_t st);

@@ -80,6 +80,34 @@ static cudaError_t sweep_k(bool fed, const DevChains &d, const SweepArgs &a, cud
 }
 
 #if !SMCB_TU_IS_STRICT
+// ---- SMCB_FP32 (fp32_mode.cuh) ----
+cudaError_t launch_evaluate_f32(const DevChains &d, const EvalOut &o, cudaStream_t st)
+{
+    const size_t smem = fp32_eval_smem(d.Npad, d.M);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t err = cudaFuncSetAttribute(k_evaluate_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    k_evaluate_f32<<<d.C, eval_threads(d.N), smem, st>>>(d, o);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_allparticle_f32(bool fed, const DevChains &d, const StepArgs &a, cudaStream_t st)
+{
+    const size_t smem = fp32_step_smem(d.Npad, d.M);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t err;
+    int threads = ((d.N + 31) / 32) * 32;
+    threads = threads > 256 ? 256 : (threads < 64 ? 64 : threads);
+    if (fed) {
+        if ((err = cudaFuncSetAttribute(k_allparticle_f32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        k_allparticle_f32<true><<<d.C, threads, smem, st>>>(d, a);
+    } else {
+        if ((err = cudaFuncSetAttribute(k_allparticle_f32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+        k_allparticle_f32<false><<<d.C, threads, smem, st>>>(d, a);
+    }
+    return cudaGetLastError();
+}
+
 // N > 512: one block per chain (sweep_block.cuh)
 static cudaError_t sweep_block_launch(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
 {

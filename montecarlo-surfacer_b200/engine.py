@@ -9,7 +9,7 @@ import re
 
 import numpy as np
 
-FAST, STRICT = 0, 1
+FAST, STRICT, FP32 = 0, 1, 2
 WALL, PERIODIC_Z = 1, 2
 A0_DEFAULT = 5.960464477539063e-9   # SMC.h:32
 B0_DEFAULT = 2.44140625e-5          # SMC.h:33
