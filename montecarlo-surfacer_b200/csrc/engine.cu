@@ -529,7 +529,7 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
         return fail(SMCB_ERR_ARG, "sweep kernels support N <= %d (N = %d): use smcb_step_allparticle", kSweepBlockMaxN, e->N);
     if (nsweeps == 0) return SMCB_OK;
     // stale running energy: the FAST warp-per-chain kernels take it from their own cache rebuild, the others need an evaluation
-    const bool kernel_refreshes = mode == SMCB_FAST && e->N <= kSweepMaxN;
+    const bool kernel_refreshes = mode == SMCB_FAST && e->N <= kSweepMaxN;     // the warp-per-chain FAST kernels take E from their cache rebuild
     if (!e->energy_valid && !kernel_refreshes && (rc = refresh_energy(e, mode))) return rc;
     SweepArgs a{};
     a.refresh_E = (!e->energy_valid && kernel_refreshes) ? 1 : 0;
