@@ -523,8 +523,6 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
     if (nsweeps < 0) return fail(SMCB_ERR_ARG, "nsweeps < 0");
     if (mode == SMCB_FP32) return fail(SMCB_ERR_ARG, "SMCB_FP32 covers the static evaluation and the all-particle step; the sweep runs in SMCB_FAST or SMCB_STRICT");
     if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "bad mode %d", mode);
-    if (e->N > kSweepMaxN && mode == SMCB_STRICT)
-        return fail(SMCB_ERR_ARG, "the STRICT (bit-exact) sweep kernel supports N <= %d (N = %d): use SMCB_FAST", kSweepMaxN, e->N);
     if (e->N > kSweepBlockMaxN)
         return fail(SMCB_ERR_ARG, "sweep kernels support N <= %d (N = %d): use smcb_step_allparticle", kSweepBlockMaxN, e->N);
     if (nsweeps == 0) return SMCB_OK;
@@ -627,8 +625,6 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
     if (nsteps <= 0) return fail(SMCB_ERR_ARG, "nsteps must be positive");
     if (mode != SMCB_FAST && mode != SMCB_STRICT) return fail(SMCB_ERR_ARG, "smcb_sweep_host runs in SMCB_FAST or SMCB_STRICT (got mode %d)", mode);
     if (kernel != 0 && kernel != 1) return fail(SMCB_ERR_ARG, "kernel: 0 = sweep (oneParticleMoves), 1 = all-particle step");
-    if (kernel == 0 && e->N > kSweepMaxN && mode == SMCB_STRICT)
-        return fail(SMCB_ERR_ARG, "the STRICT (bit-exact) sweep kernel supports N <= %d (N = %d): use SMCB_FAST", kSweepMaxN, e->N);
     if (kernel == 0 && e->N > kSweepBlockMaxN) return fail(SMCB_ERR_ARG, "sweep kernels support N <= %d (N = %d)", kSweepBlockMaxN, e->N);
     if (kernel == 1 && (size_t)(6 * e->Npad + 256) * sizeof(double) > 227 * 1024) return fail(SMCB_ERR_ARG, "N = %d does not fit one CTA's shared memory", e->N);
     if (gather && !e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");

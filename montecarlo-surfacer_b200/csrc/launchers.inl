@@ -134,6 +134,20 @@ cudaError_t SMCB_CAT(launch_sweep_, SMCB_TU_SUFFIX)(bool fed, const DevChains &d
 {
 #if !SMCB_TU_IS_STRICT
     if (d.N > kSweepMaxN) return sweep_block_launch(fed, d, a, st);
+#else
+    if (d.N > kSweepMaxN) {                      // the bit-exact sweep beyond one warp's registers: one block per chain
+        const size_t smem = StrictBlockSmem::bytes(d.Npad);
+        if (smem > 227 * 1024) return cudaErrorInvalidValue;
+        cudaError_t err;
+        if (fed) {
+            if ((err = cudaFuncSetAttribute(k_sweep_block_strict<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+            k_sweep_block_strict<true><<<d.C, 256, smem, st>>>(d, a);
+        } else {
+            if ((err = cudaFuncSetAttribute(k_sweep_block_strict<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+            k_sweep_block_strict<false><<<d.C, 256, smem, st>>>(d, a);
+        }
+        return cudaGetLastError();
+    }
 #endif
     const int k = d.Npad / 32;
     if (k <= 1) return sweep_k<1>(fed, d, a, st);

@@ -207,8 +207,8 @@ void oneParticleMoves(double *R, double *Rn, const double *W, double L, double L
     int32_t acc = 0;
     SMCB_DO(smcb_set_positions(h, R));
     SMCB_DO(smcb_set_chain_energy(h, U));
-    /* the bit-exact kernel covers N <= 512; larger systems run the FAST block kernel (same chain, 1e-12 per trial) */
-    SMCB_DO(smcb_sweep_traced(h, 1, N <= 512 ? SMCB_STRICT : SMCB_FAST, displ, &offset, u, &Etrace, &acc));
+    /* bit-exact arithmetic at every size: one warp per chain up to N = 512, one block per chain beyond */
+    SMCB_DO(smcb_sweep_traced(h, 1, SMCB_STRICT, displ, &offset, u, &Etrace, &acc));
     SMCB_DO(smcb_get_positions(h, R));
     memcpy(Rn, R, 3 * N * sizeof(double));        /* accepted: R <- Rn, rejected: Rn <- R; equal at the end */
     *j += acc;

@@ -270,8 +270,35 @@ def test_fast_sweep_large_N_block_kernel(orc, N, A):
         assert np.all(np.abs(E - Erec) <= 1e-9 * np.maximum(1.0, np.abs(Erec)))
         np.testing.assert_array_equal(Et[-1], E)
         assert at.sum() > 0 and np.all(at <= N)
-        with pytest.raises(smcb.SmcbError):                 # bit-exact mode is the warp kernel, N <= 512
-            eng.sweep(1, smcb.STRICT)
+
+
+@pytest.mark.parametrize("N,A,nsweeps", [(600, 0.3, 4), (1024, 0.05, 3), (2000, 1.1, 1)])
+def test_strict_block_sweep_bit_exact_beyond_512(orc, N, A, nsweeps):
+    """the bit-exact sweep for N > 512 (csrc/sweep_block_strict.cuh, one block per chain): free-running against the
+    oracle's oneParticleMoves on the same fed numbers - accept flags, positions and running energy identical"""
+    M, T = 3, 1.1
+    L, Lz = 33.0, 240.0
+    s = make_sys(N, M, L, Lz)
+    W = GOLDEN_W_M3.copy()
+    nchains = 2
+    rng = np.random.default_rng(N)
+    R0 = mixed_configs(N, L, Lz, nchains, seed=11 * N, orc=orc)
+    streams = np.stack([make_stream(N, nsweeps, rng) for _ in range(nchains)], axis=1)
+    displ, off, u = expand_streams(orc, N, A, streams)
+    with smcb.Engine(nchains, N, M) as eng:
+        eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
+        eng.set_positions(R0)
+        eng.refresh_energy(smcb.STRICT)
+        E0 = eng.chain_state()[0]
+        acc = eng.sweep_fed(displ, off, u, mode=smcb.STRICT, want_accepted=True)
+        R = eng.get_positions()
+        E, na, nt = eng.chain_state()
+    assert acc.sum() > 0
+    for c in range(nchains):
+        Ro, Eo, tot, flags = _oracle_run(orc, s, R0[c], W, A, T, displ[:, c], off[:, c], u[:, c], E0[c])
+        np.testing.assert_array_equal(acc[:, c], flags, err_msg=f"accept flags chain {c}")
+        np.testing.assert_array_equal(R[c], Ro, err_msg=f"positions chain {c}")
+        assert E[c] == Eo and na[c] == tot and nt[c] == nsweeps * N
 
 
 def test_block_sweep_N4096_and_bulk_mode(orc):
