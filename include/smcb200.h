@@ -271,6 +271,9 @@ int smcb_last_pair_counts(smcb_engine *e, uint64_t *pairs_total, uint64_t *pairs
  * position, SMC.c:300-321); the FAST kernels cache the old-position terms and screen in packed FP32, the all-particle
  * kernel visits every unordered pair once, so they execute fewer - this is the count behind roofline.frac_executed */
 int smcb_last_pair_tests(smcb_engine *e, uint64_t *pair_tests_executed);
+/* (debug) how the trials of the last FAST sweep launch split over the paths of k_sweep_spec: 12 counters, zero unless the
+ * library was built with -DSMCB_SPEC_STATS (profiles/spec_stats.py) */
+int smcb_debug_sweep_stats(smcb_engine *e, uint64_t *stats12);
 /* FP64 FMA peak of this device measured with a dependent-free DFMA kernel; TFLOP/s */
 int smcb_measure_fp64_peak(smcb_engine *e, double *tflops, float *ms);
 /* raw device pointers for the stream-resident benchmark path (positions SoA

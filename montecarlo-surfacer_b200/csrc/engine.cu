@@ -93,7 +93,7 @@ struct smcb_engine {
     double e_lo = -8.0, e_hi = 2.0;
     float last_ms = 0.f;
     int last_launches = 0;
-    unsigned long long last_pairs[3] = {0, 0, 0};
+    unsigned long long last_pairs[16] = {0};
     int sweep_dense = 0;                    // the last FAST sweep launch found > 2 % of the pairs inside the cutoff
 
     DevChains chains()
@@ -192,7 +192,7 @@ int smcb_create(smcb_engine **out, int device, int nchains, int N, int M)
         a = cudaStreamCreateWithFlags(&e->pstream[p], cudaStreamNonBlocking);
         if (a == cudaSuccess) a = cudaEventCreateWithFlags(&e->pev[p], cudaEventDisableTiming);
     }
-    if (a == cudaSuccess) a = cudaMallocHost(&e->pairs_pinned, 3 * sizeof(unsigned long long));
+    if (a == cudaSuccess) a = cudaMallocHost(&e->pairs_pinned, 16 * sizeof(unsigned long long));
     if (a == cudaSuccess) a = cudaMallocHost(&e->flag_pinned, sizeof(int));
     if (a == cudaSuccess) a = e->extent.ensure((size_t)2 * nchains);
     if (a == cudaSuccess) a = e->extent_flag.ensure(1);
@@ -201,13 +201,13 @@ int smcb_create(smcb_engine **out, int device, int nchains, int N, int M)
     if (a == cudaSuccess) a = e->E.ensure(nchains);
     if (a == cudaSuccess) a = e->nacc.ensure(nchains);
     if (a == cudaSuccess) a = e->ntri.ensure(nchains);
-    if (a == cudaSuccess) a = e->pairs.ensure(3);
+    if (a == cudaSuccess) a = e->pairs.ensure(16);
     if (a == cudaSuccess) a = e->totals.ensure((size_t)kTot * nchains);
     if (a == cudaSuccess) a = e->rbin.ensure((size_t)nchains * N);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->E.p, 0, nchains * sizeof(double), e->stream);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->nacc.p, 0, nchains * sizeof(long long), e->stream);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->ntri.p, 0, nchains * sizeof(long long), e->stream);
-    if (a == cudaSuccess) a = cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream);
+    if (a == cudaSuccess) a = cudaMemsetAsync(e->pairs.p, 0, 16 * sizeof(unsigned long long), e->stream);
     if (a == cudaSuccess) a = cudaMemsetAsync(e->rbin.p, 0, (size_t)nchains * N * sizeof(int), e->stream);
     if (a == cudaSuccess) a = cudaStreamSynchronize(e->stream);
     if (a != cudaSuccess) {
@@ -507,7 +507,7 @@ int smcb_reset_counters(smcb_engine *e)
 static int finish_timed(smcb_engine *e, int launches)
 {
     CK(cudaEventRecord(e->ev1, e->stream));
-    CK(cudaMemcpyAsync(e->last_pairs, e->pairs.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->last_pairs, e->pairs.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
     e->last_launches = launches;
@@ -554,7 +554,7 @@ static int sweep_common(smcb_engine *e, int nsweeps, int mode, bool fed, const d
         CK(e->cache_out.ensure((size_t)e->C * 5 * e->Npad));
         a.cache_out = e->cache_out.p;
     }
-    CK(cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->pairs.p, 0, 16 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     const DevChains d = e->chains();
     a.dense_hint = e->sweep_dense;
@@ -646,7 +646,7 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
         CK(e->eval_tickets.ensure(C));
         CK(cudaMemsetAsync(e->eval_tickets.p, 0, C * sizeof(unsigned), e->stream));
     }
-    CK(cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->pairs.p, 0, 16 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     CK(cudaEventRecord(e->pstart, e->stream));
     GatherArgs g{};
@@ -712,7 +712,7 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
         CK(cudaStreamWaitEvent(e->stream, e->pev[p], 0));
     }
     CK(cudaEventRecord(e->ev1, e->stream));
-    CK(cudaMemcpyAsync(e->pairs_pinned, e->pairs.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->pairs_pinned, e->pairs.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->flag_pinned, e->extent_flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
@@ -722,7 +722,7 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
         e->have_pos = false;
         return fail(SMCB_ERR_ARG, "positions contain NaN or coordinates more than 2^20 box lengths from the origin");
     }
-    for (int k = 0; k < 3; k++) e->last_pairs[k] = e->pairs_pinned[k];
+    for (int k = 0; k < 16; k++) e->last_pairs[k] = e->pairs_pinned[k];
     e->last_launches = parts * 3 + (gather ? 3 : 0);
     if (kernel == 0 && mode == SMCB_FAST) e->sweep_dense = e->last_pairs[1] * 50ull > e->last_pairs[0] ? 1 : 0;
     e->step += (uint64_t)nsteps;
@@ -761,7 +761,7 @@ static int step_common(smcb_engine *e, int nsteps, int mode, bool fed, const dou
     }
     if (lnap) { CK(e->stage.ensure(sc > (size_t)e->C * 3 * e->N ? sc : (size_t)e->C * 3 * e->N)); a.lnap = e->stage.p; }
     if (accepted) { CK(e->fed_acc.ensure(sc)); a.accepted = e->fed_acc.p; }
-    CK(cudaMemsetAsync(e->pairs.p, 0, 3 * sizeof(unsigned long long), e->stream));
+    CK(cudaMemsetAsync(e->pairs.p, 0, 16 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     const DevChains d = e->chains();
     CK(mode == SMCB_STRICT ? launch_allparticle_strict(fed, d, a, e->stream)
@@ -1191,6 +1191,14 @@ int smcb_last_pair_tests(smcb_engine *e, uint64_t *pair_tests_executed)
 {
     if (!e) return fail(SMCB_ERR_ARG, "null engine");
     if (pair_tests_executed) *pair_tests_executed = e->last_pairs[2];
+    return SMCB_OK;
+}
+
+// path statistics of k_sweep_spec (12 counters; all zero unless the library was built with -DSMCB_SPEC_STATS)
+int smcb_debug_sweep_stats(smcb_engine *e, uint64_t *stats12)
+{
+    if (!e || !stats12) return fail(SMCB_ERR_ARG, "null argument");
+    for (int k = 0; k < 12; k++) stats12[k] = e->last_pairs[3 + k];
     return SMCB_OK;
 }
 

@@ -107,6 +107,12 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
     double dE = 0.0;                                 // per-lane share of the running energy (owner-committed trials)
     int nacc = 0;
     unsigned cnt = 0;                                // per-lane, < 2^32 per launch
+#ifdef SMCB_SPEC_STATS
+    unsigned st[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};    // path statistics (profiles/spec_stats.py), warp-uniform
+#define SMCB_ST(i, v) st[i] += (v)
+#else
+#define SMCB_ST(i, v)
+#endif
     unsigned nscr = (unsigned)N;                     // N-particle screens executed (warp-uniform); the cache rebuild ran N
     const RngId id{a.rng.k0, a.rng.k1, a.rng.chain0 + (uint32_t)chain};
 
@@ -257,6 +263,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
 
                 // ================= phase 4: resolve in visiting order =================
                 unsigned A = 0;                          // trials of this segment accepted so far
+                SMCB_ST(0, te - tb); SMCB_ST(11, __popc(__ballot_sync(FULL, mine && nb0 > 0)));
                 unsigned genmask = 0;                    // trials that went through the general path
                 unsigned dirty = 0;                      // particles of the visited slot whose caches were touched by an accepted trial
                 // the partners of particle m's CURRENT (old) position lose their pair terms with m (force on j from m = -g d);
@@ -309,6 +316,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                         }
                         A |= cm;
                         nacc += __popc(cm);
+                        SMCB_ST(1, __popc(cm));
                         __syncwarp();
                     }
                     if (f >= te) break;
@@ -316,13 +324,15 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     cur = t + 1;
                     // with the epoch's commits known: does trial t's speculation stand?
                     const unsigned confb = __ballot_sync(FULL, pending && (lite || p_bad || isdirty || (X & A) != 0u));
-                    if (!((confb >> t) & 1u) && !((__ballot_sync(FULL, p_acc) >> t) & 1u)) continue;    // a valid rejection
+                    if (!((confb >> t) & 1u) && !((__ballot_sync(FULL, p_acc) >> t) & 1u)) { SMCB_ST(8, 1); continue; }    // a valid rejection
                     const int n = 32 * slot + t;
                     const unsigned okmask = validmask & ~((lane == t) ? 1u : 0u);
                     const int nbm = s.nb[n];
                     if (!((confb >> t) & 1u)) {
                         // ---- the speculation of trial t stands and it accepts: its owner commits it
+                        SMCB_ST(2, 1); SMCB_ST(10, __shfl_sync(FULL, pj, t) >= 0 ? 1 : 0);
                         if (nbm) {                       // the old partners forget this particle
+                            SMCB_ST(9, 1);
                             __syncwarp();
                             dirty |= __ballot_sync(FULL, drop_old_partners(n, okmask));
                             __syncwarp();
@@ -347,6 +357,16 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     }
                     // ---- general path: trial t is evaluated by the whole warp against the CURRENT state
                     genmask |= 1u << t;
+#ifdef SMCB_SPEC_STATS
+                    {
+                        const bool bad_t = __shfl_sync(FULL, (int)p_bad, t) != 0, multi_t = __shfl_sync(FULL, p_np, t) > 1;
+                        st[3]++;
+                        if (lite) st[4]++;
+                        else if (bad_t && multi_t) st[5]++;
+                        else if (bad_t) st[6]++;
+                        else if ((dirty >> t) & 1u) st[7]++;
+                    }
+#endif
                     const bool reuse = !((dirty >> t) & 1u);        // its cached force is untouched: the proposal of phase 1 stands
                     __syncwarp();
                     const double dX = fma(s.cfx[n], AoT, __shfl_sync(FULL, g0, t));
@@ -500,6 +520,9 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
             atomicAdd(d.pair_counts, (unsigned long long)a.nsweeps * 2ull * N * (N - 1));
             atomicAdd(d.pair_counts + 1, tot);
             atomicAdd(d.pair_counts + 2, (unsigned long long)nscr * (unsigned long long)(N - 1));
+#ifdef SMCB_SPEC_STATS
+            for (int i = 0; i < 12; i++) atomicAdd(d.pair_counts + 3 + i, (unsigned long long)st[i]);
+#endif
         }
     }
 }

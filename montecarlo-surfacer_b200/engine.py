@@ -113,6 +113,7 @@ def load_library():
         "smcb_last_kernel_ms": [P, C.POINTER(C.c_float), C.POINTER(C.c_int)],
         "smcb_last_pair_counts": [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
         "smcb_last_pair_tests": [P, C.POINTER(C.c_uint64)],
+        "smcb_debug_sweep_stats": [P, P],
         "smcb_sweep_host": [P, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P],
         "smcb_obs_allreduce_teardown": [],
         "smcb_tune_step_size": [P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int],
@@ -396,6 +397,11 @@ class Engine:
         a = C.c_uint64()
         self._ck(self.lib.smcb_last_pair_tests(self._h, C.byref(a)))
         return a.value
+
+    def debug_sweep_stats(self):
+        a = np.zeros(12, dtype=np.uint64)
+        self._ck(self.lib.smcb_debug_sweep_stats(self._h, _ptr(a)))
+        return a
 
     def measure_fp64_peak(self):
         t, ms = C.c_double(), C.c_float()
