@@ -230,6 +230,10 @@ int smcb_obs_get(smcb_engine *e, uint64_t *counters, double *moments);          
  * the block to / from caller-provided DEVICE buffers (same layout). */
 int smcb_obs_export_device(smcb_engine *e, void *counters_dev, void *moments_dev);
 int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void *moments_dev);
+/* export + smcb_obs_reset in one ASYNCHRONOUS step on the engine's stream (smcb_stream): returns at once, so that the
+ * caller's all-reduce of the exported delta - ordered after the engine's stream with an event - runs under the next
+ * sweep launch instead of in front of it */
+int smcb_obs_export_reset_async(smcb_engine *e, void *counters_dev, void *moments_dev);
 /* One process driving several GPUs (one engine per GPU): sum the observable blocks of the n engines
  * in place with NCCL over NVLink - one ncclAllReduce(ncclUint64) of the counters and one
  * ncclAllReduce(ncclFloat64) of the moments, the only collective of the path - so that every engine

@@ -928,6 +928,24 @@ int smcb_obs_export_device(smcb_engine *e, void *counters_dev, void *moments_dev
     return SMCB_OK;
 }
 
+// The delta-reduce step without a host round trip: the block is copied out and the accumulators are zeroed (Rbin kept)
+// on the engine's stream; the call returns at once.  The caller orders its collective after the engine's stream (an event
+// recorded on smcb_stream(e)) and may launch the next sweep immediately: the all-reduce then runs under it.
+int smcb_obs_export_reset_async(smcb_engine *e, void *counters_dev, void *moments_dev)
+{
+    int rc = check(e);
+    if (rc) return rc;
+    if (!e->counters.p) return fail(SMCB_ERR_STATE, "observable block not allocated");
+    if (!counters_dev || !moments_dev) return fail(SMCB_ERR_ARG, "null device buffer");
+    const size_t nc = e->u64_per_group() * e->ngroups * sizeof(uint64_t), nm = e->f64_per_group() * e->ngroups * sizeof(double);
+    CK(cudaMemcpyAsync(counters_dev, e->counters.p, nc, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemcpyAsync(moments_dev, e->moments.p, nm, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaMemsetAsync(e->counters.p, 0, nc, e->stream));
+    CK(cudaMemsetAsync(e->moments.p, 0, nm, e->stream));
+    e->obs_reduced = false;
+    return SMCB_OK;
+}
+
 int smcb_obs_import_device(smcb_engine *e, const void *counters_dev, const void *moments_dev)
 {
     int rc = check(e);

@@ -32,11 +32,17 @@ static void smcb_die(const char *where)
 }
 #define SMCB_DO(call) do { if ((call) != SMCB_OK) smcb_die(#call); } while (0)
 
+static smcb_engine *g_pt = NULL;         /* one chain of TWO molecules: the single-point surface routines */
+static smcb_chain_params g_pt_par;
+static double g_pt_W[2 * M * M];
+static int g_pt_have = 0;
+
 void smcb_dropin_shutdown(void)
 {
     if (g_one) smcb_destroy(g_one);
-    g_one = NULL;
-    g_one_have = 0;
+    if (g_pt) smcb_destroy(g_pt);
+    g_one = g_pt = NULL;
+    g_one_have = g_pt_have = 0;
 }
 
 int smcb_dropin_replicas(void)
@@ -80,6 +86,26 @@ static smcb_engine *one_chain(double L, double Lz, double T, double A, const dou
         g_one_have = 1;
     }
     return g_one;
+}
+
+/* wallsEnergySingle / wallsForce take ONE point: a two-molecule chain holds it next to a dummy far outside every
+ * cutoff (z is not periodic with the wall on), instead of N copies of the point in the N-molecule engine */
+static smcb_engine *one_point(double rx, double ry, double rz, double L, double Lz, const double *W)
+{
+    if (!g_pt) {
+        SMCB_DO(smcb_create(&g_pt, dropin_device(), 1, 2, M));
+        if (!g_one) atexit(smcb_dropin_shutdown);
+    }
+    const smcb_chain_params p = make_params(L, Lz, 1.0, 1.0, 1);
+    if (!(g_pt_have && memcmp(&p, &g_pt_par, sizeof p) == 0 && memcmp(W, g_pt_W, sizeof g_pt_W) == 0)) {
+        SMCB_DO(smcb_set_params(g_pt, &p, 1, W, 1, 1));
+        g_pt_par = p;
+        memcpy(g_pt_W, W, sizeof g_pt_W);
+        g_pt_have = 1;
+    }
+    const double r[6] = {rx, ry, rz, rx, ry, rz + 1000.0 * (L > Lz ? L : Lz)};
+    SMCB_DO(smcb_set_positions(g_pt, r));
+    return g_pt;
 }
 
 /* --------------------------------------------------------- LJ routines (SMC.c:557-720) ---------- */
@@ -133,10 +159,8 @@ double pressure(const double *r, double L, double Lz)
 /* ------------------------------------------------- molecule-surface routines (SMC.c:729-895) ----- */
 double wallsEnergySingle(double rx, double ry, double rz, const double *W, double L, double Lz)
 {
-    static double r[3 * N], e[N];
-    for (int n = 0; n < N; n++) { r[3 * n] = rx; r[3 * n + 1] = ry; r[3 * n + 2] = rz; }
-    smcb_engine *h = one_chain(L, Lz, 1.0, 1.0, W);
-    SMCB_DO(smcb_set_positions(h, r));
+    double e[2];
+    smcb_engine *h = one_point(rx, ry, rz, L, Lz, W);
     SMCB_DO(smcb_evaluate(h, SMCB_STRICT, NULL, NULL, e, NULL, NULL, NULL, NULL, NULL));
     return e[0];
 }
@@ -145,10 +169,8 @@ double wallsEnergySingle(double rx, double ry, double rz, const double *W, doubl
 void wallsForce(double rx, double ry, double rz, const double *W, double L, double Lz,
                 double *Fx, double *Fy, double *Fz)
 {
-    static double r[3 * N], f[3 * N];
-    for (int n = 0; n < N; n++) { r[3 * n] = rx; r[3 * n + 1] = ry; r[3 * n + 2] = rz; }
-    smcb_engine *h = one_chain(L, Lz, 1.0, 1.0, W);
-    SMCB_DO(smcb_set_positions(h, r));
+    double f[6];
+    smcb_engine *h = one_point(rx, ry, rz, L, Lz, W);
     SMCB_DO(smcb_evaluate(h, SMCB_STRICT, NULL, NULL, NULL, f, NULL, NULL, NULL, NULL));
     /* the reference starts from the caller's value and adds term by term; the engine returns the
        sum formed from 0 in the same order, so add it as one term */

@@ -117,6 +117,7 @@ def load_library():
         "smcb_sweep_host": [P, P, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P],
         "smcb_obs_allreduce_teardown": [],
         "smcb_tune_step_size": [P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int],
+        "smcb_obs_export_reset_async": [P, P, P],
         "smcb_get_step_sizes": [P, P],
         "smcb_measure_fp64_peak": [P, dp, C.POINTER(C.c_float)],
         "smcb_device_positions": [P, C.POINTER(P), C.POINTER(C.c_size_t), C.POINTER(C.c_int)],
@@ -311,6 +312,10 @@ class Engine:
 
     def step_allparticle(self, nsteps, mode=FAST):
         self._ck(self.lib.smcb_step_allparticle(self._h, nsteps, mode))
+
+    def obs_export_reset_async(self, counters_ptr, moments_ptr):
+        """device pointers (e.g. torch tensors' data_ptr()); asynchronous on the engine's stream (Engine.stream())"""
+        self._ck(self.lib.smcb_obs_export_reset_async(self._h, C.c_void_p(counters_ptr), C.c_void_p(moments_ptr)))
 
     def tune_step_size(self, kernel="sweep", mode=FAST, target=0.5, rounds=8, nsteps_per_round=10):
         """smcb_tune_step_size: per-chain A adapted towards the target acceptance; returns the A array"""

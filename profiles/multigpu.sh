@@ -15,7 +15,7 @@ import json, sys
 try:
     d = json.load(open(sys.argv[2]))
     print(f"{sys.argv[1]:14s} n_gpus {d['n_gpus']} scaling {d['scaling']:6s} value {d['value']:.4e} ms/step {d['ms_per_step']:.3f} kernel {d['kernel_ms_per_step']:.3f} "
-          f"gather {d['gather_ms_per_step']:.3f} allreduce {d['allreduce_ms_per_step']:.3f} e2e {d['e2e']['value']:.4e}")
+          f"gather {d['gather_ms_per_step']:.3f} allreduce {d['allreduce_ms_per_step']:.3f} (exposed {d.get('allreduce_exposed_ms_per_step', 0):.3f}) e2e {d['e2e']['value']:.4e}")
 except Exception as ex:
     print(sys.argv[1], "no line:", ex)
 PY

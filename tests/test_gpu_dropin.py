@@ -174,7 +174,7 @@ def test_batched_c_driver_runs(tmp_path):
     r = subprocess.run([exe, "64", "40", "120", "40", "1.1", "2"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     out = dict(line.split(" ", 1) for line in r.stdout.strip().splitlines() if " " in line)
-    head = r.stdout.splitlines()[0].split()
+    head = next(l for l in r.stdout.splitlines() if l.startswith("gpus ")).split()      # (NCCL prints its banner first on multi-GPU boxes)
     ngpu, chains, gathers, samples = int(head[1]), int(head[3]), int(head[7]), int(head[9])
     assert chains == 64 * ngpu and gathers == 3 and samples == chains * gathers
     mass, expected = int(out["mass"].split()[0]), int(out["mass"].split()[2])
