@@ -105,8 +105,17 @@ __device__ __forceinline__ void pairs_f32(const BoxF &b, const ConfF &c, int N, 
 {
     float e = 0.f, v = 0.f;
     fx = fy = fz = 0.f;
+    // a pair far outside the cutoff is recognised from the leading parts alone (their separation is off by < 1e-5 of L):
+    // only the candidates within 1.01 rc pay for the full hi+lo separation
+    const float rc2_pre = b.rc2 * 1.0201f + 1e-3f;
 #pragma unroll 4
     for (int j = 0; j < N; j++) {
+        {
+            const float ax = wrapf(x.hi - c.xh[j], b.L, b.invL), ay = wrapf(y.hi - c.yh[j], b.L, b.invL);
+            float az = z.hi - c.zh[j];
+            if (PZ) az = wrapf(az, b.Lz, b.invLz);
+            if (!(fmaf(az, az, fmaf(ay, ay, ax * ax)) < rc2_pre)) continue;
+        }
         const float dx = sepwrapf(x.hi, x.lo, c.xh[j], c.xl[j], b.L, b.invL);
         const float dy = sepwrapf(y.hi, y.lo, c.yh[j], c.yl[j], b.L, b.invL);
         const float dz = PZ ? sepwrapf(z.hi, z.lo, c.zh[j], c.zl[j], b.Lz, b.invLz) : sepf(z.hi, z.lo, c.zh[j], c.zl[j]);
