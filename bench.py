@@ -162,9 +162,10 @@ def run_reference(nsteps, warmup, min_step_s=0.25, fast=False):
     timed ones of at least min_step_s each (a step of 40 sweeps is 80 ms of CPU work: too short to time from outside)"""
     w = RefWorkers(fast)
     try:
-        t40 = w.step(40)                                    # also the first warm-up step
+        w.step(40)                                          # cold start (page faults, frequency ramp): not a calibration
+        t40 = w.step(40)
         nsweeps = int(max(40, np.ceil(40 * min_step_s / max(t40, 1e-4))))
-        for _ in range(max(0, warmup - 1)):
+        for _ in range(max(1, warmup - 1)):
             w.step(nsweeps)
         total = sum(w.step(nsweeps) for _ in range(nsteps))
     finally:
