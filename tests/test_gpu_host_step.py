@@ -232,3 +232,37 @@ def test_positions_that_cannot_be_screened_are_refused():
             eng.set_positions(bad)
         eng.set_positions(R)                         # the engine is usable afterwards
         eng.sweep(1, smcb.FAST)
+
+
+def test_sweep_host_with_per_chain_parameters_and_late_params():
+    """the pipelined call on a parameter GRID (one smcb_chain_params per chain: every block must see its own slice),
+    and positions uploaded BEFORE the parameters (the screen's extent bound is computed when L arrives)"""
+    N, C = 108, 1040
+    R, L, Lz = _start(N, C, seed=12)
+    shard = smcb.shard_chains(C, 1, 0)
+    params, ngroups = smcb.grid_chain_params(shard, [0.8, 1.1, 1.4], [200.0, 240.0], [0], L=L)
+    with smcb.Engine(C, N, 3) as eng:
+        eng.set_positions(R)                                   # before set_params
+        eng.set_params(params, GOLDEN_W_M3, ngroups=ngroups)
+        eng.set_rng(21, 0, 0)
+        eng.sweep(3, smcb.FAST)
+        eng.gather()
+        R1, (E1, na1, _), o1 = eng.get_positions(), eng.chain_state(), eng.obs_get()
+    with smcb.Engine(C, N, 3) as eng:
+        eng.set_params(params, GOLDEN_W_M3, ngroups=ngroups)
+        eng.set_rng(21, 0, 0)
+        R2 = R.copy()
+        E2, na2 = np.empty(C), np.empty(C, dtype=np.int64)
+        eng.sweep_host(R2, 3, smcb.FAST, gather=True, E=E2, naccept=na2)
+        o2 = eng.obs_get()
+    np.testing.assert_array_equal(R2, R1)
+    np.testing.assert_array_equal(na2, na1)
+    assert np.all(np.abs(E2 - E1) <= 1e-12 * np.maximum(1.0, np.abs(E1)))
+    assert len(o1) == len(o2) == ngroups
+    for g in range(ngroups):
+        for k in ("D", "Mu", "zprof", "ehist"):
+            np.testing.assert_array_equal(o2[g][k], o1[g][k])
+        assert o2[g]["nsamples"] == o1[g]["nsamples"] > 0
+    # chains at different temperatures accept differently: the slices were not mixed up
+    acc = np.array([na1[g::ngroups].mean() for g in range(ngroups)])       # global chain g sits on grid point g % ngroups
+    assert acc.max() - acc.min() > 0
