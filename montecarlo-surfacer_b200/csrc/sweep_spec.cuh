@@ -527,8 +527,13 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
     }
 }
 
+#ifdef SMCB_SPEC_MAXREG
+#define SMCB_SPEC_BOUNDS __maxnreg__(SMCB_SPEC_MAXREG)
+#else
+#define SMCB_SPEC_BOUNDS __launch_bounds__(32, (K <= 8 ? SMCB_SPEC_MINB : 8))
+#endif
 template <int K, bool FED>
-__global__ void __launch_bounds__(32, (K <= 8 ? SMCB_SPEC_MINB : 8)) k_sweep_spec(DevChains d, SweepArgs a)
+__global__ void SMCB_SPEC_BOUNDS k_sweep_spec(DevChains d, SweepArgs a)
 {
     if (chain_params(d, blockIdx.x).flags & SMCB_PERIODIC_Z) sweep_spec_body<K, FED, true>(d, a);
     else sweep_spec_body<K, FED, false>(d, a);
