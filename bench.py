@@ -73,6 +73,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (thermalised gas, all-particle kernel, droplet)")
+    ap.add_argument("--tune-step", type=float, default=0.0,
+                    help="before the timed legs, adapt every chain's A to this acceptance (smcb_tune_step_size); 0 = keep the configured A")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="batched/bulk workloads: weak = --chains (8192) chains PER GPU; strong = that many chains IN TOTAL, "
                          "sharded over the GPUs (north_star: 1->8 GPUs on 8192 chains x N=256)")
@@ -497,6 +499,9 @@ def main():
 
     fp64_peak, _ = eng.measure_fp64_peak()
     W = max(args.warmup, 3)
+    A_tuned = None
+    if args.tune_step > 0:
+        A_tuned = float(np.median(eng.tune_step_size(args.kernel, mode, target=args.tune_step, rounds=12, nsteps_per_round=max(2, min(S, 20)))))
     main = timed_leg(args.kernel, args.steps, W, sample_clocks=True)
 
     # ---- end to end through the C-ABI with host buffers (every rank, max over ranks) ----------
@@ -617,7 +622,7 @@ def main():
                                     if grid else f"{int(total_largeN)} chains x N={N} with wall in total (BASELINE configs[4]), {Cn} on this rank")
                                    + f", {args.kernel} kernel, {args.mode}",
                        "chains_per_gpu": Cn, "N": N, "M": M_SITES, "L": Lb if bulk else L_BOX, "Lz": Lb if bulk else LZ_BOX,
-                       "T": 1.0 if bulk else TEMP, "A": A,
+                       "T": 1.0 if bulk else TEMP, "A": A if A_tuned is None else A_tuned,
                        "sweeps_per_step": S, "start": ("initializeBox fcc lattice" if args.start == "lattice" else "condensed droplet on the wall") + " + warm-up steps",
                        "l2": "flushed between timed steps (256 MB write)", "rng": "Philox4x32-10",
                        "parallelism": f"chains sharded x{world}, NCCL all-reduce of the observable block only (per step, of the step's delta, "
@@ -626,6 +631,7 @@ def main():
             "allreduce_ms_per_step": main["allreduce_ms_per_step"], "allreduce_exposed_ms_per_step": main["allreduce_exposed_ms_per_step"],
             "wall_s_timed_region": main["wall_s"],
             "pairs_in_cutoff_frac": main["pairs_in_cutoff_frac"], "acceptance": main["acceptance"],
+            "msd_per_chain_step": main["msd_per_chain_step"], "msd_per_s": main["msd_per_s"],
             "roofline": {"bound": "fp64", "achieved": main["achieved_tflops"], "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": main["achieved_tflops"] / fp64_peak, "frac_nominal": main["achieved_tflops"] / fp64_peak,
                          "frac_executed": main["executed_tflops"] / fp64_peak,
