@@ -634,8 +634,10 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
     CK(e->stage.ensure((size_t)C * 3 * N));
     if (kernel == 1) { CK(e->F.ensure(cn3)); CK(e->Fn.ensure(cn3)); CK(e->dl.ensure(cn3)); }
     if (gather) CK(e->chain_mom.ensure((size_t)C * 5));
-    int parts = smcb_engine::kParts;
-    while (parts > 1 && C / parts < 256) parts /= 2;             // small batches: the copies are not worth splitting
+    // blocks of chains: enough of them to hide the copies (>= ~12 MB each way per block, a quarter of a millisecond of
+    // PCIe), never so many that a block's kernels underfill the GPU or the launches outnumber the work
+    int parts = (int)std::min<size_t>(smcb_engine::kParts, std::max<size_t>(1, ((size_t)C * 3 * N * sizeof(double)) / (12u << 20)));
+    while (parts > 1 && C / parts < 256) parts /= 2;
     int eparts = 1;                                               // blocks per chain of the FAST evaluation, decided per block size
     {
         DevChains dd = sub_chains(e, 0, (C + parts - 1) / parts);

@@ -16,9 +16,9 @@ def _start(N, C, seed=3):
     return np.stack([R0 + 0.3 * rng.standard_normal(3 * N) for _ in range(C)]), L, Lz
 
 
-@pytest.mark.parametrize("kernel,C,N,A", [("sweep", 1100, 108, 1.1), ("sweep", 40, 256, 1.1), ("allparticle", 1030, 108, 2e-4)])
+@pytest.mark.parametrize("kernel,C,N,A", [("sweep", 6100, 256, 1.1), ("sweep", 40, 256, 1.1), ("allparticle", 4300, 256, 2e-4)])
 def test_sweep_host_equals_the_separate_calls(kernel, C, N, A):
-    """one pipelined call over four chain blocks == set_positions + sweep + gather + get_positions + chain_state on
+    """one pipelined call over several chain blocks (6100 x N=256 = 37 MB: three blocks; 40 chains: one) == set_positions + sweep + gather + get_positions + chain_state on
     the whole batch: positions and accept counts bit-identical, energies to 1e-12 (the energy refresh sums per block),
     observable counters identical"""
     R, L, Lz = _start(N, C)
@@ -56,7 +56,7 @@ def test_sweep_host_equals_the_separate_calls(kernel, C, N, A):
 def test_sweep_host_positions_match_whole_batch():
     """positions after the pipelined call are bit-identical to the whole-batch path (kept apart from the test
     above so a failure names the quantity)"""
-    N, C = 108, 600
+    N, C = 256, 8200            # 50 MB of positions: four chain blocks
     R, L, Lz = _start(N, C, seed=9)
     par = smcb.default_params(L=L, Lz=Lz, T=1.1, A=1.1)
     with smcb.Engine(C, N, 3) as eng:
@@ -237,7 +237,7 @@ def test_positions_that_cannot_be_screened_are_refused():
 def test_sweep_host_with_per_chain_parameters_and_late_params():
     """the pipelined call on a parameter GRID (one smcb_chain_params per chain: every block must see its own slice),
     and positions uploaded BEFORE the parameters (the screen's extent bound is computed when L arrives)"""
-    N, C = 108, 1040
+    N, C = 256, 4200            # two chain blocks
     R, L, Lz = _start(N, C, seed=12)
     shard = smcb.shard_chains(C, 1, 0)
     params, ngroups = smcb.grid_chain_params(shard, [0.8, 1.1, 1.4], [200.0, 240.0], [0], L=L)
