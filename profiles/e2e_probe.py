@@ -1,3 +1,5 @@
+"""profiles/e2e_probe.py - what a host-buffer step costs piece by piece (8192 chains x N=256): the pipelined call with and
+without the gather, the sweeps alone, and the individual synchronous entry points.  Run on the GPU box."""
 import importlib, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/profiles')
@@ -14,7 +16,6 @@ eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=T), smcb.REFERENCE_WALL_M3
 eng.obs_configure(64, -8.0, 2.0)
 eng.broadcast_positions(R0); eng.set_rng(12345, 0, 0)
 host_R = torch.empty((C, 3*N), dtype=torch.float64).pin_memory().numpy()
-eng.get_positions(host_R) if False else None
 host_R[:] = eng.get_positions()
 hE = torch.empty(C, dtype=torch.float64).pin_memory().numpy(); hna = torch.empty(C, dtype=torch.int64).pin_memory().numpy(); hnt = torch.empty(C, dtype=torch.int64).pin_memory().numpy()
 for w in range(3): eng.sweep_host(host_R, S, smcb.FAST, gather=True, E=hE, naccept=hna, ntrials=hnt)
