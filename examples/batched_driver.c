@@ -66,6 +66,21 @@ int main(int argc, char **argv)
     for (int k = 0; k < lay.nz; k++) { printf(" %llu", (unsigned long long)zprof[k]); mass += zprof[k]; }
     printf("\nmass %llu expected %llu\n", (unsigned long long)mass, (unsigned long long)nsamp * N);
     free(cnt); free(mom);
+
+    /* A driver that keeps its configurations in HOST memory (as sMC keeps R, SMC.c:44, 117, 195) advances them with one
+       call per step: upload, E <- energy + wallsEnergy, `lapse` sweeps, one gather, download - the chain blocks' copies
+       overlap each other's kernels inside.  The all-reduced block above is final: reset it before gathering again. */
+    double *R = malloc((size_t)chains * 3 * N * sizeof *R), *Ec = malloc((size_t)chains * sizeof *Ec);
+    int64_t *na = malloc((size_t)chains * sizeof *na), *nt = malloc((size_t)chains * sizeof *nt);
+    CHECK(smcb_get_positions(eng[0], R));
+    CHECK(smcb_obs_reset(eng[0]));
+    CHECK(smcb_reset_counters(eng[0]));
+    CHECK(smcb_sweep_host(eng[0], R, lapse, SMCB_FAST, /*kernel: the sweep*/ 0, /*gather*/ 1, Ec, na, nt));
+    long long acc = 0, tri = 0;
+    for (int c = 0; c < chains; c++) { acc += na[c]; tri += nt[c]; }
+    printf("host_step chains %d sweeps %d acceptance %.4f E0 %.6f\n", chains, lapse, tri ? (double)acc / (double)tri : 0.0, Ec[0]);
+    const int host_ok = tri == (long long)chains * lapse * N;
+    free(R); free(Ec); free(na); free(nt);
     for (int g = 0; g < ngpu; g++) smcb_destroy(eng[g]);
-    return mass == nsamp * (uint64_t)N ? 0 : 2;
+    return mass == nsamp * (uint64_t)N && host_ok ? 0 : 2;
 }

@@ -181,6 +181,8 @@ def test_batched_c_driver_runs(tmp_path):
     assert mass == expected == samples * 108
     acc = float(out["mean_E"].split()[4])
     assert 0.8 < acc <= 1.0
+    host = out["host_step"].split()                       # smcb_sweep_host from plain C: "chains 64 sweeps 40 acceptance 0.95 E0 ..."
+    assert int(host[1]) == 64 and int(host[3]) == 40 and 0.8 < float(host[5]) <= 1.0 and np.isfinite(float(host[7]))
 
 
 def test_reference_main_unchanged_N4096(tmp_path):
