@@ -648,6 +648,12 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
         CK(e->eval_tickets.ensure(C));
         CK(cudaMemsetAsync(e->eval_tickets.p, 0, C * sizeof(unsigned), e->stream));
     }
+    // an error return below must not leave the block streams running behind the caller's back (the next call on the
+    // engine's own stream would not be ordered after them): drain the device on every early exit
+    struct Drain {
+        bool armed = true;
+        ~Drain() { if (armed) cudaDeviceSynchronize(); }
+    } drain;
     CK(cudaMemsetAsync(e->pairs.p, 0, 16 * sizeof(unsigned long long), e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     CK(cudaEventRecord(e->pstart, e->stream));
@@ -717,6 +723,7 @@ extern "C" int smcb_sweep_host(smcb_engine *e, double *R, int nsteps, int mode, 
     CK(cudaMemcpyAsync(e->pairs_pinned, e->pairs.p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(e->flag_pinned, e->extent_flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    drain.armed = false;                     // every block stream has been joined into the engine's stream
     CK(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
     if (*e->flag_pinned) {
         CK(cudaMemsetAsync(e->extent_flag.p, 0, sizeof(int), e->stream));
