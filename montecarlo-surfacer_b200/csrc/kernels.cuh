@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(32, (K <= 8 ? 16 : 8)) k_sweep(DevChains d, Sw
 #include "sweep_spec.cuh"
 #include "allparticle_fast.cuh"
 #include "sweep_block.cuh"
+#include "sweep_block_spec.cuh"
 #include "sweep_block_strict.cuh"
 #ifdef SMCB_MISC_KERNELS      // non-template kernels: one definition, in kernels_fast.cu
 #include "fp32_mode.cuh"

@@ -111,6 +111,24 @@ cudaError_t launch_allparticle_f32(bool fed, const DevChains &d, const StepArgs 
 // N > 512: one block per chain (sweep_block.cuh)
 static cudaError_t sweep_block_launch(bool fed, const DevChains &d, const SweepArgs &a, cudaStream_t st)
 {
+    // default: the batch-speculative kernel, one warp per trial (sweep_block_spec.cuh); SMCB_BLOCK_SWEEP=serial keeps
+    // the trial-by-trial block kernel below reachable for comparison
+    const char *which = getenv("SMCB_BLOCK_SWEEP");
+    if (!(which && strcmp(which, "serial") == 0)) {
+        int threads = SMCB_BLOCK_SPEC_THREADS;
+        if (const char *env = getenv("SMCB_BLOCK_SWEEP_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= SMCB_BLOCK_SPEC_THREADS && v % 32 == 0) threads = v; }
+        const size_t smem = BlockSpecSmem::bytes(d.Npad);
+        if (smem > 227 * 1024 || BlockSpecSmem::nf(d.Npad) / 64 > 16 * kBlockSpecWords) return cudaErrorInvalidValue;
+        cudaError_t err;
+        if (fed) {
+            if ((err = cudaFuncSetAttribute(k_sweep_block_spec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+            k_sweep_block_spec<true><<<d.C, threads, smem, st>>>(d, a);
+        } else {
+            if ((err = cudaFuncSetAttribute(k_sweep_block_spec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+            k_sweep_block_spec<false><<<d.C, threads, smem, st>>>(d, a);
+        }
+        return cudaGetLastError();
+    }
     int threads = 256;
     if (const char *env = getenv("SMCB_BLOCK_SWEEP_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 512 && v % 32 == 0) threads = v; }
     // a thread keeps two hit bits per screen iteration in one 32-bit word: at most 16 iterations (block_eval_point)

@@ -63,6 +63,7 @@ struct ChainSmem {
 struct ScreenConsts {
     float rc2s;               // (rc/L + margin)^2: cutoff in box units, inflated by the FP32 error bound below
     float zper, inv_zper;     // Lz/L and L/Lz (bulk mode only)
+    float interior;           // a point with |x|/L below this needs no minimum image along x (same for y), see below
 };
 
 // FP32 error bound of a box-unit separation: operands are rounded to float, differences and the wrap add one more
@@ -81,6 +82,12 @@ __device__ __forceinline__ ScreenConsts make_screen(const Box &b, const float *e
     ScreenConsts sc;
     sc.rc2s = (float)(rcs * rcs * (1.0 + 1e-6));
     sc.zper = (float)(b.Lz * b.invL); sc.inv_zper = (float)(b.L * b.invLz);
+    // A point farther than the (inflated) cutoff from both periodic faces along an axis: every molecule of the primary
+    // cell (|x|/L <= 1/2) whose minimum-image separation along that axis is inside the cutoff has it as its PLAIN
+    // difference (|plain| > 1/2 means the image is at least 1 - (|point| + 1/2) >= cutoff away), and a plain difference
+    // is never shorter than the minimum image.  The screen may then skip the wrap of that axis for the whole pass.
+    // Only when the chain was uploaded inside the primary cell (extent 1/2); otherwise no point qualifies.
+    sc.interior = (axy <= 0.5) ? (float)(0.5 - rcs * (1.0 + 1e-6) - 4.0 * eps) : -1.f;
     return sc;
 }
 
@@ -130,8 +137,9 @@ struct Slots {
     }
 };
 
-// which of the lane's K slots are within the (inflated) cutoff of the point (px,py,pz), box units
-template <int K, bool PZ>
+// which of the lane's K slots are within the (inflated) cutoff of the point (px,py,pz), box units.
+// WX / WY = false: the caller knows the point is interior along that axis (ScreenConsts::interior), no wrap needed.
+template <int K, bool PZ, bool WX = true, bool WY = true>
 __device__ __forceinline__ unsigned screen_slots(const ScreenConsts &sc, float px, float py, float pz, const Slots<K> &q)
 {
     const float2 ax = make_float2(px, px), ay = make_float2(py, py), az = make_float2(pz, pz);
@@ -140,9 +148,9 @@ __device__ __forceinline__ unsigned screen_slots(const ScreenConsts &sc, float p
 #pragma unroll
     for (int k = 0; k < Slots<K>::KP; k++) {
         float2 sx = sub2(ax, q.x[k]);
-        sx = sub2(sx, sub2(add2(sx, MG), MG));
+        if (WX) sx = sub2(sx, sub2(add2(sx, MG), MG));
         float2 sy = sub2(ay, q.y[k]);
-        sy = sub2(sy, sub2(add2(sy, MG), MG));
+        if (WY) sy = sub2(sy, sub2(add2(sy, MG), MG));
         float2 sz = sub2(az, q.z[k]);
         if (PZ) {
             const float2 t = mul2(sz, make_float2(sc.inv_zper, sc.inv_zper));

@@ -272,6 +272,55 @@ def test_fast_sweep_large_N_block_kernel(orc, N, A):
         assert at.sum() > 0 and np.all(at <= N)
 
 
+@pytest.mark.parametrize("N,A,threads", [(1500, 0.05, 1024), (1024, 0.3, 256), (4096, 0.01, 1024), (650, 1.1, 512)])
+def test_block_spec_sweep_equals_serial_block_sweep(orc, N, A, threads, monkeypatch):
+    """the batch-speculative block sweep (csrc/sweep_block_spec.cuh: one warp per trial, a batch of trials evaluated
+    against the same state, the valid prefix committed) against the trial-by-trial block kernel (SMCB_BLOCK_SWEEP=serial)
+    on the same fed numbers over several sweeps: the accept flags of every trial are identical and the positions and
+    energies agree to rounding (the two kernels add a point's pair terms in different orders), in a gas, a dense
+    droplet (most batches are cut short by an accepted neighbour) and at N = 4096; free-running Philox sweeps likewise"""
+    M, T = 3, 1.1
+    L, Lz = 33.0, 240.0
+    W = GOLDEN_W_M3.copy()
+    nchains, nsweeps = 3, 3
+    rng = np.random.default_rng(N)
+    if N == 4096:
+        X = orc.fcc_lattice(L, Lz, 16, 16, 4)
+        R0 = np.stack([X + 0.02 * rng.standard_normal(3 * N) for _ in range(nchains)])
+    else:
+        R0 = mixed_configs(N, L, Lz, nchains, seed=5 * N, orc=orc)
+    streams = np.stack([make_stream(N, nsweeps, rng) for _ in range(nchains)], axis=1)
+    displ, off, u = expand_streams(orc, N, A, streams)
+    out = {}
+    for which in ("serial", "spec"):
+        monkeypatch.setenv("SMCB_BLOCK_SWEEP", which)
+        if which == "spec":
+            monkeypatch.setenv("SMCB_BLOCK_SWEEP_THREADS", str(threads))
+        with smcb.Engine(nchains, N, M) as eng:
+            eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
+            eng.set_positions(R0)
+            eng.refresh_energy(smcb.FAST)
+            acc = eng.sweep_fed(displ, off, u, mode=smcb.FAST, want_accepted=True)
+            R, (E, na, nt) = eng.get_positions(), eng.chain_state()
+            pt = eng.last_pair_counts()
+            eng.set_positions(R0)
+            eng.refresh_energy(smcb.FAST)
+            eng.set_rng(21, 0, 0)
+            eng.reset_counters()
+            Et, at = eng.sweep_traced(3, smcb.FAST)
+            out[which] = (acc, R, E, na, nt, Et, at, eng.get_positions(), pt)
+    a, b = out["serial"], out["spec"]
+    assert a[0].sum() > 0
+    np.testing.assert_array_equal(a[0], b[0])
+    assert rel_err(b[1], a[1], floor=1.0) < 1e-11
+    assert np.all(np.abs(a[2] - b[2]) <= 1e-10 * np.maximum(1.0, np.abs(a[2])))
+    np.testing.assert_array_equal(a[3], b[3]); np.testing.assert_array_equal(a[4], b[4])
+    np.testing.assert_array_equal(a[6], b[6])                       # accepted moves per Philox sweep
+    assert np.all(np.abs(a[5] - b[5]) <= 1e-10 * np.maximum(1.0, np.abs(a[5])))
+    assert rel_err(b[7], a[7], floor=1.0) < 1e-11
+    assert tuple(b[8]) == tuple(a[8])                                # nominal and in-cutoff pairs of the committed trials: the same counts
+
+
 @pytest.mark.parametrize("N,A,nsweeps", [(600, 0.3, 4), (1024, 0.05, 3), (2000, 1.1, 1)])
 def test_strict_block_sweep_bit_exact_beyond_512(orc, N, A, nsweeps):
     """the bit-exact sweep for N > 512 (csrc/sweep_block_strict.cuh, one block per chain): free-running against the
