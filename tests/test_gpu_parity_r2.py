@@ -231,13 +231,38 @@ def _reference_replica(c):
     return np.mean(es), acc / (100 * N), R[2::3].mean()
 
 
+def _independent_replica(c):
+    """the same protocol with the oracle's sweep driven by INDEPENDENT Gaussians (numpy) instead of vecBoxMuller's coupled
+    pairs: the Markov kernel the acceptance rule of SMC.c:326-335 is derived for"""
+    orc = Oracle()
+    s = make_sys(N, M, L, LZ)
+    W = GOLDEN_W_M3.copy()
+    R, _ = orc.initialize_box(L, LZ, N)
+    E = orc.energy(s, R) + orc.walls_energy(s, R, W)
+    rng = np.random.default_rng(770000 + c)
+    es, acc = [], 0
+    for k in range(250):
+        Ak = 2 * A if k < 150 else A
+        a_, E = orc.sweep(s, R, W, Ak, T, rng.standard_normal(3 * N) * np.sqrt(2 * Ak), int(rng.integers(0, 2**31)), rng.random(N), E)
+        if k >= 150:
+            acc += a_
+            if k % 10 == 9:
+                es.append(E)
+    return np.mean(es), acc / (100 * N), R[2::3].mean()
+
+
 def test_replica_statistics_headline_geometry(orc):
     """N = 256 in main.c's box, T = A = 1.1: many SHORT replica chains from the start lattice - 150 sweeps with 2A
     (sMC's thermalisation) then 100 production sweeps - on the reference's sampler (128 chains on the host cores) and
     on the FAST kernel with Philox streams (2048 chains).  Same Markov kernel => same distribution at equal time:
-    mean energy over the production window, acceptance ratio and the mean height of the gas agree within 2 sigma.
+    mean energy over the production window and acceptance ratio agree within 2 sigma.
     (Both sides are seeded, so the outcome is deterministic; 1024 further reference chains give <E> = -4.955 +- 0.020
-    against the kernel's -4.956.)"""
+    against the kernel's -4.956.)
+    The mean HEIGHT of the gas is compared with the oracle's sweep driven by independent Gaussians, not with the
+    reference's stream: vecBoxMuller couples the two numbers of a pair (E[a0^2 a1] = -0.5 sigma^3), the acceptance rule
+    assumes an isotropic proposal, and with that stream the gas drifts up by 0.3 sigma over this protocol (DESIGN §2,
+    tests/studies/boxmuller_pairing.py: 16.855 +- 0.028 against 16.519 +- 0.027 over 4096 chains each) - the engine
+    reproduces that drift when it is FED the reference's numbers, and must not show it on its own stream."""
     import multiprocessing as mp
     import os
     W = GOLDEN_W_M3.copy()
@@ -245,7 +270,8 @@ def test_replica_statistics_headline_geometry(orc):
     n_eq, n_prod, every = 150, 100, 10
     with mp.get_context("fork").Pool(min(16, len(os.sched_getaffinity(0)))) as pool:
         ref = np.array(pool.map(_reference_replica, range(1000, 1128)))
-    ref_E, ref_acc, ref_z = ref[:, 0], ref[:, 1], ref[:, 2]
+        ind = np.array(pool.map(_independent_replica, range(128)))
+    ref_E, ref_acc = ref[:, 0], ref[:, 1]
     C = 2048
     with smcb.Engine(C, N, M) as eng:
         eng.set_params(smcb.default_params(L=L, Lz=LZ, T=T, A=A), W)
@@ -270,4 +296,5 @@ def test_replica_statistics_headline_geometry(orc):
 
     close(ref_E, gE, "<E>")
     close(ref_acc, gacc, "acceptance")
-    close(ref_z, gz, "mean height")
+    close(ind[:, 2], gz, "mean height (independent Gaussians)")
+    close(ind[:, 0], gE, "<E> (independent Gaussians)")
