@@ -115,18 +115,22 @@ static cudaError_t sweep_block_launch(bool fed, const DevChains &d, const SweepA
     // the trial-by-trial block kernel below reachable for comparison
     const char *which = getenv("SMCB_BLOCK_SWEEP");
     if (!(which && strcmp(which, "serial") == 0)) {
-        int threads = SMCB_BLOCK_SPEC_THREADS;
-        if (const char *env = getenv("SMCB_BLOCK_SWEEP_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= SMCB_BLOCK_SPEC_THREADS && v % 32 == 0) threads = v; }
+        // one trial per warp; SMCB_BLOCK_SPEC_TPW=2: two (512 threads, every molecule pair loaded once for both points; slower)
+        int tpw = 1;
+        if (const char *env = getenv("SMCB_BLOCK_SPEC_TPW")) { const int v = atoi(env); if (v == 1 || v == 2) tpw = v; }
+        int threads = 1024 / tpw;
+        if (const char *env = getenv("SMCB_BLOCK_SWEEP_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 1024 / tpw && v % 32 == 0) threads = v; }
         const size_t smem = BlockSpecSmem::bytes(d.Npad);
         if (smem > 227 * 1024 || BlockSpecSmem::nf(d.Npad) / 64 > 16 * kBlockSpecWords) return cudaErrorInvalidValue;
         cudaError_t err;
-        if (fed) {
-            if ((err = cudaFuncSetAttribute(k_sweep_block_spec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-            k_sweep_block_spec<true><<<d.C, threads, smem, st>>>(d, a);
-        } else {
-            if ((err = cudaFuncSetAttribute(k_sweep_block_spec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-            k_sweep_block_spec<false><<<d.C, threads, smem, st>>>(d, a);
-        }
+#define SMCB_LAUNCH_BLOCK_SPEC(FEDV, TPWV)                                                                                                     \
+        do {                                                                                                                                   \
+            if ((err = cudaFuncSetAttribute(k_sweep_block_spec<FEDV, TPWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
+            k_sweep_block_spec<FEDV, TPWV><<<d.C, threads, smem, st>>>(d, a);                                                                  \
+        } while (0)
+        if (fed) { if (tpw == 2) SMCB_LAUNCH_BLOCK_SPEC(true, 2); else SMCB_LAUNCH_BLOCK_SPEC(true, 1); }
+        else     { if (tpw == 2) SMCB_LAUNCH_BLOCK_SPEC(false, 2); else SMCB_LAUNCH_BLOCK_SPEC(false, 1); }
+#undef SMCB_LAUNCH_BLOCK_SPEC
         return cudaGetLastError();
     }
     int threads = 256;

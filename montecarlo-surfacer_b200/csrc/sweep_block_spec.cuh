@@ -58,19 +58,19 @@ __device__ __forceinline__ bool screen_near(const ScreenConsts &sc, float ax, fl
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < sc.rc2s;
 }
 
-// one packed screen iteration: the molecule pair j2 against the point; two hit bits are shifted into w from the right.
-// r2 >= 0, so as integers the two floats compare like the numbers do: (bits(r2) - bits(rc2s)) is negative exactly for a
-// hit, and a funnel shift moves that sign bit into w - two integer instructions per molecule, no predicates.
+// one packed screen iteration: a molecule pair (two molecules per float2) against the point; two hit bits are shifted
+// into w from the right.  r2 >= 0, so as integers the two floats compare like the numbers do: (bits(r2) - bits(rc2s))
+// is negative exactly for a hit, and a funnel shift moves that sign bit into w - two integer instructions per molecule.
 template <bool PZ, bool WX, bool WY>
-__device__ __forceinline__ void block_spec_screen_pair(const ScreenConsts &sc, const float2 *X2, const float2 *Y2, const float2 *Z2, int j2,
+__device__ __forceinline__ void block_spec_screen_pair(const ScreenConsts &sc, float2 mx, float2 my, float2 mz,
                                                        float2 ax, float2 ay, float2 az, int rcbits, unsigned &w)
 {
     const float2 MG = make_float2(12582912.f, 12582912.f);
-    float2 sx = sub2(ax, X2[j2]);
+    float2 sx = sub2(ax, mx);
     if (WX) sx = sub2(sx, sub2(add2(sx, MG), MG));
-    float2 sy = sub2(ay, Y2[j2]);
+    float2 sy = sub2(ay, my);
     if (WY) sy = sub2(sy, sub2(add2(sy, MG), MG));
-    float2 sz = sub2(az, Z2[j2]);
+    float2 sz = sub2(az, mz);
     if (PZ) {
         const float2 t = mul2(sz, make_float2(sc.inv_zper, sc.inv_zper));
         sz = fma2(sub2(add2(t, MG), MG), make_float2(-sc.zper, -sc.zper), sz);
@@ -80,108 +80,167 @@ __device__ __forceinline__ void block_spec_screen_pair(const ScreenConsts &sc, c
     w = __funnelshift_l((unsigned)(__float_as_int(r2.y) - rcbits), w, 1);
 }
 
-// one pass of the packed-FP32 screen over the chain for the point q (box units).  Lane l tests the molecule pairs
-// j2 = l + 32 it; 16 iterations fill one 32-bit word, FIRST tested molecule in the TOP bit; hq[c] holds words 2c
-// (upper half) and 2c + 1, so that a count-leading-zeros walk visits the lane's hits in ascending molecule index.
-template <bool PZ, bool WX, bool WY>
+// one pass of the packed-FP32 screen over the chain for NP points q (box units) at once: every molecule pair is loaded
+// once and tested against all of them.  Lane l tests the molecule pairs j2 = l + 32 it; 16 iterations fill one 32-bit
+// word, FIRST tested molecule in the TOP bit; hq[p][c] holds words 2c (upper half) and 2c + 1 of point p, so that a
+// count-leading-zeros walk visits the lane's hits in ascending molecule index.
+template <bool PZ, bool WX, bool WY, int NP>
 __device__ __forceinline__ void block_spec_screen(const ScreenConsts &sc, const BlockSpecSmem &s, int nit, int lane,
-                                                  float qx, float qy, float qz, unsigned long long (&hq)[kBlockSpecWords / 2])
+                                                  const float (&qx)[NP], const float (&qy)[NP], const float (&qz)[NP],
+                                                  unsigned long long (&hq)[NP][kBlockSpecWords / 2])
 {
-    const float2 ax = make_float2(qx, qx), ay = make_float2(qy, qy), az = make_float2(qz, qz);
+    float2 ax[NP], ay[NP], az[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        ax[p] = make_float2(qx[p], qx[p]); ay[p] = make_float2(qy[p], qy[p]); az[p] = make_float2(qz[p], qz[p]);
+        hq[p][0] = 0ull; hq[p][1] = 0ull; hq[p][2] = 0ull;
+    }
     const float2 *X2 = reinterpret_cast<const float2 *>(s.fx), *Y2 = reinterpret_cast<const float2 *>(s.fy),
                  *Z2 = reinterpret_cast<const float2 *>(s.fz);
     const int rcbits = __float_as_int(sc.rc2s);
-    hq[0] = 0ull; hq[1] = 0ull; hq[2] = 0ull;
 #pragma unroll 1
     for (int cp = 0; 32 * cp < nit; cp++) {           // two words per pass: the unrolled body stays small (instruction cache)
-        unsigned long long v = 0ull;
+        unsigned long long v[NP];
+#pragma unroll
+        for (int p = 0; p < NP; p++) v[p] = 0ull;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int c = 2 * cp + h;
-            unsigned w = 0;
+            unsigned w[NP];
+#pragma unroll
+            for (int p = 0; p < NP; p++) w[p] = 0u;
             const int i1 = min(16, nit - 16 * c);
             if (i1 == 16) {
 #pragma unroll
-                for (int i = 0; i < 16; i++)
-                    block_spec_screen_pair<PZ, WX, WY>(sc, X2, Y2, Z2, lane + 32 * (16 * c + i), ax, ay, az, rcbits, w);
+                for (int i = 0; i < 16; i++) {
+                    const int j2 = lane + 32 * (16 * c + i);
+                    const float2 mx = X2[j2], my = Y2[j2], mz = Z2[j2];
+#pragma unroll
+                    for (int p = 0; p < NP; p++) block_spec_screen_pair<PZ, WX, WY>(sc, mx, my, mz, ax[p], ay[p], az[p], rcbits, w[p]);
+                }
             } else if (i1 > 0) {                       // the last, partial word of a chain that is no multiple of 1024
-                for (int i = 0; i < i1; i++)
-                    block_spec_screen_pair<PZ, WX, WY>(sc, X2, Y2, Z2, lane + 32 * (16 * c + i), ax, ay, az, rcbits, w);
-                w <<= 32 - 2 * i1;
+                for (int i = 0; i < i1; i++) {
+                    const int j2 = lane + 32 * (16 * c + i);
+                    const float2 mx = X2[j2], my = Y2[j2], mz = Z2[j2];
+#pragma unroll
+                    for (int p = 0; p < NP; p++) block_spec_screen_pair<PZ, WX, WY>(sc, mx, my, mz, ax[p], ay[p], az[p], rcbits, w[p]);
+                }
+#pragma unroll
+                for (int p = 0; p < NP; p++) w[p] <<= 32 - 2 * i1;
             }
-            v = (v << 32) | (unsigned long long)w;
+#pragma unroll
+            for (int p = 0; p < NP; p++) v[p] = (v[p] << 32) | (unsigned long long)w[p];
         }
-        if (cp == 0) hq[0] = v; else if (cp == 1) hq[1] = v; else hq[2] = v;
+#pragma unroll
+        for (int p = 0; p < NP; p++) { if (cp == 0) hq[p][0] = v[p]; else if (cp == 1) hq[p][1] = v[p]; else hq[p][2] = v[p]; }
     }
 }
 
-// energy (already *4) and force of molecule `self` placed at p, against all the others and the surface, by ONE warp;
-// every lane returns the warp totals.  nin: partners inside the cutoff (warp total).
-template <bool PZ>
-__device__ __forceinline__ void warp_eval_point_smem(const Box &b, const ScreenConsts &sc, const BlockSpecSmem &s, const double *__restrict__ W,
-                                                     int N, int nit, int self, double px, double py, double pz, int lane,
-                                                     double &U, double &Fx, double &Fy, double &Fz, unsigned &nin)
+// the next hit of a lane's bit words (ascending molecule index); false when none is left
+__device__ __forceinline__ bool block_spec_next_hit(unsigned long long (&hq)[kBlockSpecWords / 2], int lane, int &j)
 {
-    const float qx = (float)(px * b.invL), qy = (float)(py * b.invL), qz = (float)(pz * b.invL);
-    // phase 1: the screen.  Lane l tests the molecule pairs j2 = l + 32 it (molecules 2 j2, 2 j2 + 1), 16 iterations
-    // fill one word of hit bits; nit = NF / 64 iterations in all, the same for every lane (the arrays are padded).
-    // The point is the same for the whole warp: the wrap of an axis along which it is interior (ScreenConsts) is
-    // dropped from the pass by a uniform branch - the screen is the packed-FP32 pipe's load of this kernel.
-    unsigned long long hq[kBlockSpecWords / 2];
-    const bool wx = !(fabsf(qx) < sc.interior), wy = !(fabsf(qy) < sc.interior);
-    if (wx) {
-        if (wy) block_spec_screen<PZ, true, true>(sc, s, nit, lane, qx, qy, qz, hq);
-        else block_spec_screen<PZ, true, false>(sc, s, nit, lane, qx, qy, qz, hq);
-    } else {
-        if (wy) block_spec_screen<PZ, false, true>(sc, s, nit, lane, qx, qy, qz, hq);
-        else block_spec_screen<PZ, false, false>(sc, s, nit, lane, qx, qy, qz, hq);
+    int o;                                             // order index of the hit: 64 per word, 2 per screen iteration
+    if (hq[0]) { const int p = __clzll((long long)hq[0]); hq[0] &= ~(0x8000000000000000ull >> p); o = p; }
+    else if (hq[1]) { const int p = __clzll((long long)hq[1]); hq[1] &= ~(0x8000000000000000ull >> p); o = 64 + p; }
+    else if (hq[2]) { const int p = __clzll((long long)hq[2]); hq[2] &= ~(0x8000000000000000ull >> p); o = 128 + p; }
+    else return false;
+    j = 2 * (lane + 32 * (o >> 1)) + (o & 1);
+    return true;
+}
+
+// energy (already *4) and force of NP molecules `self[p]` placed at p[p], each against all the others and the surface,
+// by ONE warp in one pass over the chain; every lane returns the warp totals.  nin[p]: partners inside the cutoff.
+template <bool PZ, int NP>
+__device__ __forceinline__ void warp_eval_points_smem(const Box &b, const ScreenConsts &sc, const BlockSpecSmem &s, const double *__restrict__ W,
+                                                      int N, int nit, int lane, const int (&self)[NP],
+                                                      const double (&px)[NP], const double (&py)[NP], const double (&pz)[NP],
+                                                      double (&U)[NP], double (&Fx)[NP], double (&Fy)[NP], double (&Fz)[NP], unsigned (&nin)[NP])
+{
+    float qx[NP], qy[NP], qz[NP];
+    bool wx = false, wy = false;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        qx[p] = (float)(px[p] * b.invL); qy[p] = (float)(py[p] * b.invL); qz[p] = (float)(pz[p] * b.invL);
+        wx |= !(fabsf(qx[p]) < sc.interior); wy |= !(fabsf(qy[p]) < sc.interior);
     }
-    // phase 2: the lane's hits in ascending molecule index, exact FP64 terms from the unscaled positions
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-    unsigned mine = 0;
-    for (;;) {
-        int o;                                         // order index of the hit: 64 per hq word, 2 per screen iteration
-        if (hq[0]) { const int p = __clzll((long long)hq[0]); hq[0] &= ~(0x8000000000000000ull >> p); o = p; }
-        else if (hq[1]) { const int p = __clzll((long long)hq[1]); hq[1] &= ~(0x8000000000000000ull >> p); o = 64 + p; }
-        else if (hq[2]) { const int p = __clzll((long long)hq[2]); hq[2] &= ~(0x8000000000000000ull >> p); o = 128 + p; }
-        else break;
-        const int j = 2 * (lane + 32 * (o >> 1)) + (o & 1);
-        double et, gx, gy, gz;
-        if (j != self && j < N && pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
-            v0 += et; v1 += gx; v2 += gy; v3 += gz;
-            mine++;
+    // phase 1: the screen.  The points are the same for the whole warp: the wrap of an axis along which they are
+    // interior (ScreenConsts) is dropped from the pass by a uniform branch - the screen is this kernel's load.
+    unsigned long long hq[NP][kBlockSpecWords / 2];
+    if (wx) {
+        if (wy) block_spec_screen<PZ, true, true, NP>(sc, s, nit, lane, qx, qy, qz, hq);
+        else block_spec_screen<PZ, true, false, NP>(sc, s, nit, lane, qx, qy, qz, hq);
+    } else {
+        if (wy) block_spec_screen<PZ, false, true, NP>(sc, s, nit, lane, qx, qy, qz, hq);
+        else block_spec_screen<PZ, false, false, NP>(sc, s, nit, lane, qx, qy, qz, hq);
+    }
+    // phase 2: the lane's hits in ascending molecule index, exact FP64 terms from the unscaled positions; the
+    // points take turns, so that their dependent FP64 chains overlap
+    double v[NP][4];
+    unsigned mine[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) { v[p][0] = 0.0; v[p][1] = 0.0; v[p][2] = 0.0; v[p][3] = 0.0; mine[p] = 0; }
+    if (NP == 1) {
+        int j;
+        while (block_spec_next_hit(hq[0], lane, j)) {
+            double et, gx, gy, gz;
+            if (j != self[0] && j < N && pair_exact(b, px[0], py[0], pz[0], s.x[j], s.y[j], s.z[j], et, gx, gy, gz)) {
+                v[0][0] += et; v[0][1] += gx; v[0][2] += gy; v[0][3] += gz;
+                mine[0]++;
+            }
+        }
+    } else for (;;) {
+        int j[NP];
+        bool has[NP], any = false;
+#pragma unroll
+        for (int p = 0; p < NP; p++) { has[p] = block_spec_next_hit(hq[p], lane, j[p]); has[p] = has[p] && j[p] != self[p] && j[p] < N; any |= has[p] || hq[p][0] || hq[p][1] || hq[p][2]; }
+        if (!any) break;
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            const int jj = has[p] ? j[p] : 0;
+            double dx, dy, dz;
+            const double r2 = pair_sep<false>(b, px[p], py[p], pz[p], s.x[jj], s.y[jj], s.z[jj], dx, dy, dz);
+            const bool in = has[p] && r2 < b.rc2;
+            const double i2 = fast_rcp(in ? r2 : 1.0);         // same arithmetic as pair_exact
+            const double i6 = i2 * i2 * i2;
+            const double et = fma(i6, i6, -i6);
+            const double g = i2 * i6 * fma(48.0, i6, -24.0);
+            if (in) { v[p][0] += et; v[p][1] += g * dx; v[p][2] += g * dy; v[p][3] += g * dz; mine[p]++; }
         }
     }
     __syncwarp();
-    double ew = 0.0, fzw = 0.0;
-    if (b.wall) {
-        const double dzw = wall_dz<false>(b, pz);
-        add_zwall(b, dzw, ew, fzw);                    // flat wall: uniform, added after the reduction
-        if (dzw * dzw < b.rc2) {                       // surface sites: lane m owns sites m, m + 32, ...
-            const int MM = b.M * b.M;
-            const double dw = b.L / b.M;
-            for (int m = lane; m < MM; m += 32) {
-                const int i = m / b.M, j = m - i * b.M;
-                const double dx = min_image<false>(px - i * dw, b.L, b.invL);
-                const double dy = min_image<false>(py - j * dw, b.L, b.invL);
-                const double r2w = fma(dzw, dzw, fma(dy, dy, dx * dx));
-                if (r2w < b.rc2) {
-                    const double i2 = fast_rcp(r2w);
-                    const double i6 = i2 * i2 * i2;
-                    const double a6 = W[2 * m] * i6;
-                    v0 += fma(a6, i6, -W[2 * m + 1] * i6);
-                    const double g = i2 * i6 * fma(48.0, a6, -24.0 * W[2 * m + 1]);
-                    v1 = fma(g, dx, v1); v2 = fma(g, dy, v2); v3 = fma(g, dzw, v3);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        double ew = 0.0, fzw = 0.0;
+        if (b.wall) {
+            const double dzw = wall_dz<false>(b, pz[p]);
+            add_zwall(b, dzw, ew, fzw);                // flat wall: uniform, added after the reduction
+            if (dzw * dzw < b.rc2) {                   // surface sites: lane m owns sites m, m + 32, ...
+                const int MM = b.M * b.M;
+                const double dw = b.L / b.M;
+                for (int m = lane; m < MM; m += 32) {
+                    const int i = m / b.M, jm = m - i * b.M;
+                    const double dx = min_image<false>(px[p] - i * dw, b.L, b.invL);
+                    const double dy = min_image<false>(py[p] - jm * dw, b.L, b.invL);
+                    const double r2w = fma(dzw, dzw, fma(dy, dy, dx * dx));
+                    if (r2w < b.rc2) {
+                        const double i2 = fast_rcp(r2w);
+                        const double i6 = i2 * i2 * i2;
+                        const double a6 = W[2 * m] * i6;
+                        v[p][0] += fma(a6, i6, -W[2 * m + 1] * i6);
+                        const double g = i2 * i6 * fma(48.0, a6, -24.0 * W[2 * m + 1]);
+                        v[p][1] = fma(g, dx, v[p][1]); v[p][2] = fma(g, dy, v[p][2]); v[p][3] = fma(g, dzw, v[p][3]);
+                    }
                 }
             }
         }
+        warp_sum4(lane, v[p][0], v[p][1], v[p][2], v[p][3]);
+        nin[p] += __reduce_add_sync(FULL, mine[p]);
+        U[p] = 4.0 * (v[p][0] + ew); Fx[p] = v[p][1]; Fy[p] = v[p][2]; Fz[p] = v[p][3] + fzw;
     }
-    warp_sum4(lane, v0, v1, v2, v3);
-    nin += __reduce_add_sync(FULL, mine);
-    U = 4.0 * (v0 + ew); Fx = v1; Fy = v2; Fz = v3 + fzw;
 }
 
-template <bool FED, bool PZ>
+// TPW = trials per warp: a batch is NW x TPW <= 32 trials, trial t of the batch belongs to warp t % NW, slot t / NW
+template <bool FED, bool PZ, int TPW>
 __device__ __forceinline__ void sweep_block_spec_body(const DevChains &d, const SweepArgs &a)
 {
     const int chain = blockIdx.x, N = d.N, Npad = d.Npad, tid = threadIdx.x, T_ = blockDim.x;
@@ -208,6 +267,7 @@ __device__ __forceinline__ void sweep_block_spec_body(const DevChains &d, const 
     double E = d.E[chain];                             // kept by thread 0
     int nacc = 0;
     unsigned long long cnt = 0, nscr = 0;              // thread 0
+    const int BMAX = min(32, NW * TPW);
 
     for (int sw = 0; sw < a.nsweeps; sw++) {
         const unsigned long long step = a.rng.step0 + (unsigned long long)sw;
@@ -219,66 +279,88 @@ __device__ __forceinline__ void sweep_block_spec_body(const DevChains &d, const 
         const int off = (int)(offset % N);
         int nn0 = 0;
         while (nn0 < N) {
-            const int Bn = min(NW, N - nn0);           // trials nn0 .. nn0 + Bn - 1, warp w takes trial nn0 + w
-            bool acc = false;
-            double qx = 0.0, qy = 0.0, qz = 0.0;
-            float ox = 0.f, oy = 0.f, oz = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
-            int n = 0;
-            if (warp < Bn) {
-                const int nn = nn0 + warp;
-                n = nn + off;                          // n = (nn+offset)%N  SMC.c:294
-                if (n >= N) n -= N;
-                double g0, g1, g2, ul;                 // every lane of the warp forms the same numbers
-                if (FED) {
-                    const double *dsp = a.displ + sci * 3 * N;
-                    g0 = dsp[3 * n]; g1 = dsp[3 * n + 1]; g2 = dsp[3 * n + 2];
-                    ul = a.u[sci * N + nn];
-                } else {
-                    rng_particle_gauss_f32(id, step, (uint32_t)n, g0, g1, g2);
-                    g0 *= sigma; g1 *= sigma; g2 *= sigma;
-                    ul = rng_particle_uniform(id, step, (uint32_t)n);
+            const int Bn = min(BMAX, N - nn0);         // trials nn0 .. nn0 + Bn - 1 of the sweep
+            int n[TPW], tix[TPW];
+            bool act[TPW], acc[TPW];
+            double px[TPW], py[TPW], pz[TPW], qx[TPW], qy[TPW], qz[TPW];
+            float ox[TPW], oy[TPW], oz[TPW], nx[TPW], ny[TPW], nz[TPW];
+#pragma unroll
+            for (int p = 0; p < TPW; p++) {
+                tix[p] = warp + NW * p;
+                act[p] = tix[p] < Bn;
+                n[p] = nn0 + (act[p] ? tix[p] : 0) + off;      // n = (nn+offset)%N  SMC.c:294; idle slots shadow trial 0
+                if (n[p] >= N) n[p] -= N;
+                px[p] = s.x[n[p]]; py[p] = s.y[n[p]]; pz[p] = s.z[n[p]];
+                acc[p] = false;
+            }
+            if (act[0]) {
+                double g0[TPW], g1[TPW], g2[TPW], lul[TPW];    // every lane of the warp forms the same numbers
+#pragma unroll
+                for (int p = 0; p < TPW; p++) {
+                    double ul;
+                    if (FED) {
+                        const double *dsp = a.displ + sci * 3 * N;
+                        g0[p] = dsp[3 * n[p]]; g1[p] = dsp[3 * n[p] + 1]; g2[p] = dsp[3 * n[p] + 2];
+                        ul = a.u[sci * N + nn0 + (act[p] ? tix[p] : 0)];
+                    } else {
+                        rng_particle_gauss_f32(id, step, (uint32_t)n[p], g0[p], g1[p], g2[p]);
+                        g0[p] *= sigma; g1[p] *= sigma; g2[p] *= sigma;
+                        ul = rng_particle_uniform(id, step, (uint32_t)n[p]);
+                    }
+                    lul[p] = log(ul);
                 }
-                const double px = s.x[n], py = s.y[n], pz = s.z[n];
-                double Um, Fmx, Fmy, Fmz, Un, Fnx, Fny, Fnz;
-                unsigned nin = 0;
-                warp_eval_point_smem<PZ>(b, sc, s, W, N, nit, n, px, py, pz, lane, Um, Fmx, Fmy, Fmz, nin);          // SMC.c:300-304
-                const double dX = fma(Fmx, AoT, g0), dY = fma(Fmy, AoT, g1), dZ = fma(Fmz, AoT, g2);               // SMC.c:307-309
-                qx = min_image<false>(px + dX, b.L, b.invL); qy = min_image<false>(py + dY, b.L, b.invL);           // SMC.c:311-316
-                qz = pz + dZ;
-                if (PZ) qz = min_image<false>(qz, b.Lz, b.invLz);
-                warp_eval_point_smem<PZ>(b, sc, s, W, N, nit, n, qx, qy, qz, lane, Un, Fnx, Fny, Fnz, nin);          // SMC.c:319-321
-                // SMC.c:326-335: accept iff u < exp(-(Un-Um + d.(Fn+Fm)/2 + (Fn^2-Fm^2) A/(4T))/T)
-                const double f2 = fma(Fnx, Fnx, fma(Fny, Fny, Fnz * Fnz)) - fma(Fmx, Fmx, fma(Fmy, Fmy, Fmz * Fmz));
-                const double dr = fma(dX, Fnx + Fmx, fma(dY, Fny + Fmy, dZ * (Fnz + Fmz)));
-                const double xarg = -((Un - Um) + 0.5 * dr + f2 * quarterAoT) * invT;
-                acc = (log(ul) < xarg) && (xarg > -745.1332191019411);
-                ox = s.fx[n]; oy = s.fy[n]; oz = s.fz[n];
-                nx = (float)(qx * b.invL); ny = (float)(qy * b.invL); nz = (float)(qz * b.invL);
-                // the molecules of the EARLIER trials of the batch, where they are now: in range of my old or proposed position?
-                bool hit = false;
-                if (lane < warp) {
-                    int nm = nn0 + lane + off;
-                    if (nm >= N) nm -= N;
-                    const float mx = s.fx[nm], my = s.fy[nm], mz = s.fz[nm];
-                    hit = screen_near<PZ>(sc, ox, oy, oz, mx, my, mz) || screen_near<PZ>(sc, nx, ny, nz, mx, my, mz);
+                double Um[TPW], Fmx[TPW], Fmy[TPW], Fmz[TPW], Un[TPW], Fnx[TPW], Fny[TPW], Fnz[TPW], dX[TPW], dY[TPW], dZ[TPW];
+                unsigned nin[TPW];
+#pragma unroll
+                for (int p = 0; p < TPW; p++) nin[p] = 0;
+                warp_eval_points_smem<PZ, TPW>(b, sc, s, W, N, nit, lane, n, px, py, pz, Um, Fmx, Fmy, Fmz, nin);      // SMC.c:300-304
+#pragma unroll
+                for (int p = 0; p < TPW; p++) {
+                    dX[p] = fma(Fmx[p], AoT, g0[p]); dY[p] = fma(Fmy[p], AoT, g1[p]); dZ[p] = fma(Fmz[p], AoT, g2[p]);   // SMC.c:307-309
+                    qx[p] = min_image<false>(px[p] + dX[p], b.L, b.invL); qy[p] = min_image<false>(py[p] + dY[p], b.L, b.invL);   // SMC.c:311-316
+                    qz[p] = pz[p] + dZ[p];
+                    if (PZ) qz[p] = min_image<false>(qz[p], b.Lz, b.invLz);
                 }
-                const unsigned x1 = __ballot_sync(FULL, hit);
-                if (lane == 0) {
-                    s.pq[warp] = qx; s.pq[32 + warp] = qy; s.pq[64 + warp] = qz;
-                    s.pf[warp] = nx; s.pf[32 + warp] = ny; s.pf[64 + warp] = nz;
-                    s.pdU[warp] = Un - Um;
-                    s.pacc[warp] = acc ? 1u : 0u; s.pin[warp] = nin; s.px[warp] = x1;
+                warp_eval_points_smem<PZ, TPW>(b, sc, s, W, N, nit, lane, n, qx, qy, qz, Un, Fnx, Fny, Fnz, nin);      // SMC.c:319-321
+#pragma unroll
+                for (int p = 0; p < TPW; p++) {
+                    // SMC.c:326-335: accept iff u < exp(-(Un-Um + d.(Fn+Fm)/2 + (Fn^2-Fm^2) A/(4T))/T)
+                    const double f2 = fma(Fnx[p], Fnx[p], fma(Fny[p], Fny[p], Fnz[p] * Fnz[p])) - fma(Fmx[p], Fmx[p], fma(Fmy[p], Fmy[p], Fmz[p] * Fmz[p]));
+                    const double dr = fma(dX[p], Fnx[p] + Fmx[p], fma(dY[p], Fny[p] + Fmy[p], dZ[p] * (Fnz[p] + Fmz[p])));
+                    const double xarg = -((Un[p] - Um[p]) + 0.5 * dr + f2 * quarterAoT) * invT;
+                    acc[p] = act[p] && (lul[p] < xarg) && (xarg > -745.1332191019411);
+                    ox[p] = s.fx[n[p]]; oy[p] = s.fy[n[p]]; oz[p] = s.fz[n[p]];
+                    nx[p] = (float)(qx[p] * b.invL); ny[p] = (float)(qy[p] * b.invL); nz[p] = (float)(qz[p] * b.invL);
+                    // the molecules of the EARLIER trials of the batch, where they are now: in range of my old or proposed position?
+                    bool hit = false;
+                    if (lane < tix[p]) {
+                        int nm = nn0 + lane + off;
+                        if (nm >= N) nm -= N;
+                        const float mx = s.fx[nm], my = s.fy[nm], mz = s.fz[nm];
+                        hit = screen_near<PZ>(sc, ox[p], oy[p], oz[p], mx, my, mz) || screen_near<PZ>(sc, nx[p], ny[p], nz[p], mx, my, mz);
+                    }
+                    const unsigned x1 = __ballot_sync(FULL, hit);
+                    if (lane == 0 && act[p]) {
+                        const int t = tix[p];
+                        s.pq[t] = qx[p]; s.pq[32 + t] = qy[p]; s.pq[64 + t] = qz[p];
+                        s.pf[t] = nx[p]; s.pf[32 + t] = ny[p]; s.pf[64 + t] = nz[p];
+                        s.pdU[t] = Un[p] - Um[p];
+                        s.pacc[t] = acc[p] ? 1u : 0u; s.pin[t] = nin[p]; s.px[t] = x1;
+                    }
                 }
             }
             __syncthreads();
-            if (warp < Bn) {                           // ... and where they would move to
-                bool hit = false;
-                if (lane < warp) {
-                    const float mx = s.pf[lane], my = s.pf[32 + lane], mz = s.pf[64 + lane];
-                    hit = screen_near<PZ>(sc, ox, oy, oz, mx, my, mz) || screen_near<PZ>(sc, nx, ny, nz, mx, my, mz);
+#pragma unroll
+            for (int p = 0; p < TPW; p++) {
+                if (act[p]) {                          // ... and where they would move to
+                    bool hit = false;
+                    if (lane < tix[p]) {
+                        const float mx = s.pf[lane], my = s.pf[32 + lane], mz = s.pf[64 + lane];
+                        hit = screen_near<PZ>(sc, ox[p], oy[p], oz[p], mx, my, mz) || screen_near<PZ>(sc, nx[p], ny[p], nz[p], mx, my, mz);
+                    }
+                    const unsigned x2 = __ballot_sync(FULL, hit);
+                    if (lane == 0) s.px[tix[p]] |= x2;
                 }
-                const unsigned x2 = __ballot_sync(FULL, hit);
-                if (lane == 0) s.px[warp] |= x2;
             }
             __syncthreads();
             // every trial before f saw exactly the state the sequential sweep shows it: f = the first trial with an
@@ -286,9 +368,12 @@ __device__ __forceinline__ void sweep_block_spec_body(const DevChains &d, const 
             const unsigned accmask = __ballot_sync(FULL, lane < Bn && s.pacc[lane] != 0u);
             const unsigned bad = __ballot_sync(FULL, lane < Bn && (s.px[lane] & accmask) != 0u);
             const int f = bad ? __ffs(bad) - 1 : Bn;
-            if (warp < f && acc && lane == 0) {
-                s.x[n] = qx; s.y[n] = qy; s.z[n] = qz;
-                s.fx[n] = nx; s.fy[n] = ny; s.fz[n] = nz;
+#pragma unroll
+            for (int p = 0; p < TPW; p++) {
+                if (tix[p] < f && acc[p] && lane == 0) {
+                    s.x[n[p]] = qx[p]; s.y[n[p]] = qy[p]; s.z[n[p]] = qz[p];
+                    s.fx[n[p]] = nx[p]; s.fy[n[p]] = ny[p]; s.fz[n[p]] = nz[p];
+                }
             }
             if (tid == 0) {
                 for (int w = 0; w < f; w++) {
@@ -318,14 +403,14 @@ __device__ __forceinline__ void sweep_block_spec_body(const DevChains &d, const 
     }
 }
 
-#ifndef SMCB_BLOCK_SPEC_THREADS
-#define SMCB_BLOCK_SPEC_THREADS 1024
-#endif
-template <bool FED>
-__global__ void __launch_bounds__(SMCB_BLOCK_SPEC_THREADS) k_sweep_block_spec(DevChains d, SweepArgs a)
+// TPW = 1 (default): 1024 threads, one trial per warp (64 registers).  TPW = 2 (SMCB_BLOCK_SPEC_TPW=2): 512 threads, two
+// trials per warp (128 registers), every molecule pair loaded once for both - half the shared-memory wavefronts, the
+// same instruction count, and 30 % slower: 4 warps per scheduler hide less latency than 8 (profiles/r02)
+template <bool FED, int TPW>
+__global__ void __launch_bounds__(1024 / TPW) k_sweep_block_spec(DevChains d, SweepArgs a)
 {
-    if (chain_params(d, blockIdx.x).flags & SMCB_PERIODIC_Z) sweep_block_spec_body<FED, true>(d, a);
-    else sweep_block_spec_body<FED, false>(d, a);
+    if (chain_params(d, blockIdx.x).flags & SMCB_PERIODIC_Z) sweep_block_spec_body<FED, true, TPW>(d, a);
+    else sweep_block_spec_body<FED, false, TPW>(d, a);
 }
 
 }  // namespace smcb

@@ -272,9 +272,9 @@ def test_fast_sweep_large_N_block_kernel(orc, N, A):
         assert at.sum() > 0 and np.all(at <= N)
 
 
-@pytest.mark.parametrize("N,A,threads", [(1500, 0.05, 1024), (1024, 0.3, 256), (4096, 0.01, 1024), (650, 1.1, 512)])
+@pytest.mark.parametrize("N,A,threads", [(1500, 0.05, 1024), (1024, 0.3, 256), (4096, 0.01, 512), (650, 1.1, 512), (1100, 0.2, 128)])
 def test_block_spec_sweep_equals_serial_block_sweep(orc, N, A, threads, monkeypatch):
-    """the batch-speculative block sweep (csrc/sweep_block_spec.cuh: one warp per trial, a batch of trials evaluated
+    """the batch-speculative block sweep (csrc/sweep_block_spec.cuh: one or two trials per warp, a batch of trials evaluated
     against the same state, the valid prefix committed) against the trial-by-trial block kernel (SMCB_BLOCK_SWEEP=serial)
     on the same fed numbers over several sweeps: the accept flags of every trial are identical and the positions and
     energies agree to rounding (the two kernels add a point's pair terms in different orders), in a gas, a dense
@@ -294,7 +294,8 @@ def test_block_spec_sweep_equals_serial_block_sweep(orc, N, A, threads, monkeypa
     out = {}
     for which in ("serial", "spec"):
         monkeypatch.setenv("SMCB_BLOCK_SWEEP", which)
-        if which == "spec":
+        if which == "spec":                                  # 1024 / 128 threads: one trial per warp; 512 / 256: two
+            monkeypatch.setenv("SMCB_BLOCK_SPEC_TPW", "1" if threads in (1024, 128) else "2")
             monkeypatch.setenv("SMCB_BLOCK_SWEEP_THREADS", str(threads))
         with smcb.Engine(nchains, N, M) as eng:
             eng.set_params(smcb.default_params(L=L, Lz=Lz, T=T, A=A), W)
