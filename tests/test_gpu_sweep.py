@@ -292,9 +292,9 @@ def test_block_spec_sweep_equals_serial_block_sweep(orc, N, A, threads, monkeypa
     streams = np.stack([make_stream(N, nsweeps, rng) for _ in range(nchains)], axis=1)
     displ, off, u = expand_streams(orc, N, A, streams)
     out = {}
-    for which in ("serial", "spec"):
-        monkeypatch.setenv("SMCB_BLOCK_SWEEP", which)
-        if which == "spec":                                  # 1024 / 128 threads: one trial per warp; 512 / 256: two
+    for which in ("serial", "spec", "spec again"):
+        monkeypatch.setenv("SMCB_BLOCK_SWEEP", which.split()[0])
+        if which != "serial":                                  # 1024 / 128 threads: one trial per warp; 512 / 256: two
             monkeypatch.setenv("SMCB_BLOCK_SPEC_TPW", "1" if threads in (1024, 128) else "2")
             monkeypatch.setenv("SMCB_BLOCK_SWEEP_THREADS", str(threads))
         with smcb.Engine(nchains, N, M) as eng:
@@ -310,7 +310,9 @@ def test_block_spec_sweep_equals_serial_block_sweep(orc, N, A, threads, monkeypa
             eng.reset_counters()
             Et, at = eng.sweep_traced(3, smcb.FAST)
             out[which] = (acc, R, E, na, nt, Et, at, eng.get_positions(), pt)
-    a, b = out["serial"], out["spec"]
+    a, b, b2 = out["serial"], out["spec"], out["spec again"]
+    for x, y in zip(b, b2):                                          # a data race in the batch protocol would show here
+        np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
     assert a[0].sum() > 0
     np.testing.assert_array_equal(a[0], b[0])
     assert rel_err(b[1], a[1], floor=1.0) < 1e-11
