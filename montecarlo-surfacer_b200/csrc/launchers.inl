@@ -158,6 +158,22 @@ cudaError_t SMCB_CAT(launch_sweep_, SMCB_TU_SUFFIX)(bool fed, const DevChains &d
     if (d.N > kSweepMaxN) return sweep_block_launch(fed, d, a, st);
 #else
     if (d.N > kSweepMaxN) {                      // the bit-exact sweep beyond one warp's registers: one block per chain
+        const char *which = getenv("SMCB_BLOCK_SWEEP");
+        if (!(which && strcmp(which, "serial") == 0)) {            // batch-speculative, one warp per trial (same bits)
+            const size_t smem = BlockSpecSmem::bytes(d.Npad);
+            if (smem > 227 * 1024 || BlockSpecSmem::nf(d.Npad) / 64 > 16 * kBlockSpecWords) return cudaErrorInvalidValue;
+            int threads = 512;
+            if (const char *env = getenv("SMCB_BLOCK_SWEEP_THREADS")) { const int v = atoi(env); if (v >= 64 && v <= 512 && v % 32 == 0) threads = v; }
+            cudaError_t err;
+            if (fed) {
+                if ((err = cudaFuncSetAttribute(k_sweep_block_strict_spec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+                k_sweep_block_strict_spec<true><<<d.C, threads, smem, st>>>(d, a);
+            } else {
+                if ((err = cudaFuncSetAttribute(k_sweep_block_strict_spec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+                k_sweep_block_strict_spec<false><<<d.C, threads, smem, st>>>(d, a);
+            }
+            return cudaGetLastError();
+        }
         const size_t smem = StrictBlockSmem::bytes(d.Npad);
         if (smem > 227 * 1024) return cudaErrorInvalidValue;
         cudaError_t err;

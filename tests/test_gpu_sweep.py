@@ -324,17 +324,26 @@ def test_block_spec_sweep_equals_serial_block_sweep(orc, N, A, threads, monkeypa
     assert tuple(b[8]) == tuple(a[8])                                # nominal and in-cutoff pairs of the committed trials: the same counts
 
 
-@pytest.mark.parametrize("N,A,nsweeps", [(600, 0.3, 4), (1024, 0.05, 3), (2000, 1.1, 1)])
-def test_strict_block_sweep_bit_exact_beyond_512(orc, N, A, nsweeps):
+@pytest.mark.parametrize("which", ["spec", "serial"])
+@pytest.mark.parametrize("N,A,nsweeps", [(600, 0.3, 4), (1024, 0.05, 3), (2000, 1.1, 1), (4096, 0.02, 1)])
+def test_strict_block_sweep_bit_exact_beyond_512(orc, N, A, nsweeps, which, monkeypatch):
     """the bit-exact sweep for N > 512 (csrc/sweep_block_strict.cuh, one block per chain): free-running against the
-    oracle's oneParticleMoves on the same fed numbers - accept flags, positions and running energy identical"""
+    oracle's oneParticleMoves on the same fed numbers - accept flags, positions and running energy identical.  Both
+    organisations: batch-speculative (a warp per trial, the default) and trial by trial (SMCB_BLOCK_SWEEP=serial)."""
+    if which == "serial" and N == 4096:
+        pytest.skip("covered by the batch-speculative kernel; the serial one takes long here")
+    monkeypatch.setenv("SMCB_BLOCK_SWEEP", which)
     M, T = 3, 1.1
     L, Lz = 33.0, 240.0
     s = make_sys(N, M, L, Lz)
     W = GOLDEN_W_M3.copy()
     nchains = 2
     rng = np.random.default_rng(N)
-    R0 = mixed_configs(N, L, Lz, nchains, seed=11 * N, orc=orc)
+    if N == 4096:                                           # BASELINE configs[4]: the corrected 16x16x4 fcc slab, jittered
+        X = orc.fcc_lattice(L, Lz, 16, 16, 4)
+        R0 = np.stack([X + 0.02 * rng.standard_normal(3 * N) for _ in range(nchains)])
+    else:
+        R0 = mixed_configs(N, L, Lz, nchains, seed=11 * N, orc=orc)
     streams = np.stack([make_stream(N, nsweeps, rng) for _ in range(nchains)], axis=1)
     displ, off, u = expand_streams(orc, N, A, streams)
     with smcb.Engine(nchains, N, M) as eng:
