@@ -165,7 +165,16 @@ def run_reference(nsteps, warmup, min_step_s=0.25, fast=False):
     w = RefWorkers(fast)
     try:
         w.step(40)                                          # cold start (page faults, frequency ramp): not a calibration
-        t40 = w.step(40)
+        # warm up until the host has settled: 40-sweep steps until two in a row agree within 3 % (at most ~3 s) - on a
+        # fresh box the first second runs 15-50 % slower, and a slow reference would flatter the GPU arm
+        t40, spent = w.step(40), 0.0
+        for _ in range(40):
+            t = w.step(40)
+            spent += t
+            settled = abs(t - t40) <= 0.03 * t
+            t40 = t
+            if settled or spent > 3.0:
+                break
         nsweeps = int(max(40, np.ceil(40 * min_step_s / max(t40, 1e-4))))
         for _ in range(max(1, warmup - 1)):
             w.step(nsweeps)
@@ -185,7 +194,7 @@ def reference_arm(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)"}))
         return
     nsteps = max(1, min(args.steps, 40))
-    value, cores, nsweeps, total = run_reference(nsteps, max(1, min(args.warmup, 3)))
+    value, cores, nsweeps, total = run_reference(nsteps, max(1, min(args.warmup, 3)), min_step_s=0.5)
     line = {
         "impl": "reference", "metric": "pair_interactions_per_s", "value": value, "unit": "pair-interactions/s",
         "chain_steps_per_s": value / pairs_per_sweep(N_PART), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
