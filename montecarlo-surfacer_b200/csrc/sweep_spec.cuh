@@ -13,12 +13,14 @@
 //            table in shared memory), which of the segment's own particles are in range of its proposal (po), and
 //            which of the other PROPOSALS are (pp, from a proposal-against-proposal test in the same loop)
 //   phase 3  lane t evaluates the exact FP64 pair terms of its own trial's partners (0-1 of them in the gas: a
-//            short divergent loop), adds the flat wall, and decides its trial completely (SMC.c:319-335)
+//            short divergent loop; it keeps their SUMS, up to SMCB_SPEC_MAXPARTNERS partners), adds the flat wall,
+//            and decides its trial completely (SMC.c:319-335)
 //   phase 4  the warp walks only the trials that need work, in visiting order: accepted ones are committed by
-//            their owner lane (position, caches, the one partner's caches, Newton's third law); a trial whose
+//            their owner lane (position, caches, the partners' caches by Newton's third law - one partner: from the
+//            terms the lane holds, several: formed again, only the sums were kept); a trial whose
 //            inputs were changed by an earlier accepted trial of the segment - its cached force (dirty), or the set
 //            of particles in range of its proposal ((pp | po) & accepted) - or that is near the surface or has
-//            several partners, is redone on the warp-wide general path of k_sweep_cached.  Rejected trials with
+//            more partners than that, is redone on the warp-wide general path of k_sweep_cached.  Rejected trials with
 //            valid speculation cost nothing in phase 4.
 // A trial's speculation is valid exactly when nothing it read has changed since the start of the segment, so the
 // results are those of the sequential sweep (tests: accept flags identical to the oracle's, positions and energies
@@ -45,6 +47,9 @@ struct SpecSmem {
 
 #ifndef SMCB_SPEC_MINB
 #define SMCB_SPEC_MINB 10
+#endif
+#ifndef SMCB_SPEC_MAXPARTNERS
+#define SMCB_SPEC_MAXPARTNERS 3      // a trial with up to this many partners at its proposal is decided by its own lane
 #endif
 
 template <int K, bool FED, bool PZ>
@@ -241,12 +246,12 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                                 const int j = l + 32 * sl;
                                 double et, hx, hy, hz;
                                 if (pair_exact(b, p_qx, p_qy, p_qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
-                                    pe = et; pgx = hx; pgy = hy; pgz = hz; pj = j;
+                                    pe += et; pgx += hx; pgy += hy; pgz += hz; pj = j;     // one partner: exactly its terms
                                     p_np++;
                                 }
                             }
                         }
-                        if (p_np > 1) {
+                        if (p_np > SMCB_SPEC_MAXPARTNERS) {
                             p_bad = true;
                         } else {
                             const double Um = s.ce[nl], Fmx = s.cfx[nl], Fmy = s.cfy[nl], Fmz = s.cfz[nl];   // SMC.c:300-304, cached
@@ -290,7 +295,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                 // nobody else's caches.  Each pass of the loop is an EPOCH: f = the first pending trial that needs serial
                 // work (void or possibly void speculation, or an accepted trial with partners); the accepted lonely trials
                 // before f are committed together by their owner lanes, then f is handled alone.
-                const bool lonely = mine && !p_bad && pj < 0 && nb0 == 0;
+                const bool lonely = mine && !p_bad && p_np == 0 && nb0 == 0;
                 const unsigned lowmask = (1u << lane) - 1u;
                 int cur = tb;
                 while (cur < te) {
@@ -338,18 +343,42 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                             __syncwarp();
                         }
                         if (lane == t) {
-                            if (pj >= 0) {               // the one new partner gains the pair terms (force on j from n = -g d)
+                            if (p_np == 1) {             // the one new partner gains the pair terms (force on j from n = -g d)
                                 s.ce[pj] += 4.0 * pe; s.cfx[pj] -= pgx; s.cfy[pj] -= pgy; s.cfz[pj] -= pgz;
                                 s.nb[pj] += 1;
+                            } else if (p_np > 1) {       // several: the lane holds their SUMS; each one's terms are formed again
+                                unsigned hb = my_hb;
+                                while (hb) {
+                                    const int l = __ffs(hb) - 1;
+                                    hb &= hb - 1;
+                                    unsigned m = hm[lane * 32 + l];
+                                    while (m) {
+                                        const int k = __ffs(m) - 1;
+                                        m &= m - 1;
+                                        int sl = k + rot;
+                                        if (sl >= K) sl -= K;
+                                        const int j = l + 32 * sl;
+                                        double et, hx, hy, hz;
+                                        if (pair_exact(b, p_qx, p_qy, p_qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
+                                            s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
+                                            s.nb[j] += 1;
+                                        }
+                                    }
+                                }
                             }
                             s.x[n] = p_qx; s.y[n] = p_qy; s.z[n] = p_qz;
                             s.ce[n] = 4.0 * (pe + p_ew); s.cfx[n] = pgx; s.cfy[n] = pgy; s.cfz[n] = pgz + p_fz;
-                            s.nb[n] = (unsigned short)(pj >= 0 ? 1 : 0);
+                            s.nb[n] = (unsigned short)p_np;
                             q.set(0, st_x, st_y, st_z);
                             dE += p_dU;                 // SMC.c:341, summed per lane, reduced at the end of the sweep
                         }
-                        const int pjt = __shfl_sync(FULL, pj, t);
-                        if (pjt >= 0 && (pjt >> 5) == slot) dirty |= 1u << (pjt & 31);
+                        // partners that belong to the visited slot have had their caches touched: their speculation is void.
+                        // One partner: exactly that one; several: every slot-0 molecule the screen found near the proposal
+                        // (a superset - a void speculation only costs the general path)
+                        const int pjt = __shfl_sync(FULL, pj, t), npt = __shfl_sync(FULL, p_np, t);
+                        const unsigned pot = __shfl_sync(FULL, my_po, t);
+                        if (npt == 1) { if ((pjt >> 5) == slot) dirty |= 1u << (pjt & 31); }
+                        else if (npt > 1) dirty |= pot;
                         A |= 1u << t;
                         nacc++;
                         __syncwarp();
