@@ -211,21 +211,27 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     // and the rare hit masks go to the 32x32 table with an atomicOr on the trial's row word
                     const float MGs = 12582912.f;
                     nscr += (unsigned)((te - (tb & ~1) + 1) & ~1);
+                    const float2 MG2 = make_float2(MGs, MGs), rc2 = make_float2(sc.rc2s, sc.rc2s);
+                    const float2 stx2 = make_float2(st_x, st_x), sty2 = make_float2(st_y, st_y), stz2 = make_float2(st_z, st_z);
                     for (int t2 = tb & ~1; t2 < te; t2 += 2) {
+                        // the two proposals of this iteration, one 8-byte load per component (t2 is even)
+                        const float2 ax2 = *reinterpret_cast<const float2 *>(s.stage + t2);
+                        const float2 ay2 = *reinterpret_cast<const float2 *>(s.stage + 32 + t2);
+                        const float2 az2 = *reinterpret_cast<const float2 *>(s.stage + 64 + t2);
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const int t = t2 + h;
-                            const float ax = s.stage[t], ay = s.stage[32 + t], az = s.stage[64 + t];
-                            const unsigned m = screen_slots<K, PZ>(sc, ax, ay, az, q) & validmask & ~((lane == t) ? 1u : 0u);
+                            const unsigned m = screen_slots<K, PZ>(sc, h ? ax2.y : ax2.x, h ? ay2.y : ay2.x, h ? az2.y : az2.x, q) & validmask & ~((lane == t) ? 1u : 0u);
                             if (m) { hm[t * 32 + lane] = (HM)m; atomicOr(hbrow + t, 1u << lane); }
                             my_in |= (m & 1u) << t;
-                            float dx = ax - st_x, dy = ay - st_y, dz = az - st_z;
-                            dx -= (dx + MGs) - MGs;
-                            dy -= (dy + MGs) - MGs;
-                            if (PZ) dz = fmaf((dz * sc.inv_zper + MGs) - MGs, -sc.zper, dz);
-                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            my_pp |= ((r2 < sc.rc2s) ? 1u : 0u) << t;
                         }
+                        // proposal against proposal, both trials of the iteration in one packed pass
+                        float2 dx = sub2(ax2, stx2), dy = sub2(ay2, sty2), dz = sub2(az2, stz2);
+                        dx = sub2(dx, sub2(add2(dx, MG2), MG2));
+                        dy = sub2(dy, sub2(add2(dy, MG2), MG2));
+                        if (PZ) dz = fma2(sub2(add2(mul2(dz, make_float2(sc.inv_zper, sc.inv_zper)), MG2), MG2), make_float2(-sc.zper, -sc.zper), dz);
+                        const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                        my_pp |= (((r2.x < rc2.x) ? 1u : 0u) | ((r2.y < rc2.y) ? 2u : 0u)) << t2;
                     }
                     my_pp &= ~(1u << lane);
                     __syncwarp();
