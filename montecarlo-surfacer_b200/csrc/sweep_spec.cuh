@@ -52,6 +52,33 @@ struct SpecSmem {
 #define SMCB_SPEC_MAXPARTNERS 3      // a trial with up to this many partners at its proposal is decided by its own lane
 #endif
 
+// screen_slots for phase 2: the hit bit of a slot is the SIGN of r2 - rc2 (one packed subtraction for two slots), shifted
+// into the mask by a funnel shift - 1.5 instructions per slot instead of FSETP + predicated OR.  Slots are visited from
+// the last to the first so that slot 0 ends up in bit 0.  (r2 == rc2 gives +0: no hit, like `<`.)
+template <int K, bool PZ>
+__device__ __forceinline__ unsigned screen_slots_sgn(const ScreenConsts &sc, float px, float py, float pz, const Slots<K> &q)
+{
+    const float2 ax = make_float2(px, px), ay = make_float2(py, py), az = make_float2(pz, pz);
+    const float2 MG = make_float2(12582912.f, 12582912.f), rc2 = make_float2(sc.rc2s, sc.rc2s);
+    unsigned hits = 0;
+#pragma unroll
+    for (int k = Slots<K>::KP - 1; k >= 0; k--) {
+        float2 sx = sub2(ax, q.x[k]);
+        sx = sub2(sx, sub2(add2(sx, MG), MG));
+        float2 sy = sub2(ay, q.y[k]);
+        sy = sub2(sy, sub2(add2(sy, MG), MG));
+        float2 sz = sub2(az, q.z[k]);
+        if (PZ) {
+            const float2 t = mul2(sz, make_float2(sc.inv_zper, sc.inv_zper));
+            sz = fma2(sub2(add2(t, MG), MG), make_float2(-sc.zper, -sc.zper), sz);
+        }
+        const float2 d = sub2(fma2(sz, sz, fma2(sy, sy, mul2(sx, sx))), rc2);
+        hits = __funnelshift_l(__float_as_uint(d.y), hits, 1);
+        hits = __funnelshift_l(__float_as_uint(d.x), hits, 1);
+    }
+    return hits;
+}
+
 template <int K, bool FED, bool PZ>
 __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepArgs &a)
 {
@@ -221,7 +248,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const int t = t2 + h;
-                            const unsigned m = screen_slots<K, PZ>(sc, h ? ax2.y : ax2.x, h ? ay2.y : ay2.x, h ? az2.y : az2.x, q) & validmask & ~((lane == t) ? 1u : 0u);
+                            const unsigned m = screen_slots_sgn<K, PZ>(sc, h ? ax2.y : ax2.x, h ? ay2.y : ay2.x, h ? az2.y : az2.x, q) & validmask & ~((lane == t) ? 1u : 0u);
                             if (m) { hm[t * 32 + lane] = (HM)m; atomicOr(hbrow + t, 1u << lane); }
                             my_in |= (m & 1u) << t;
                         }
