@@ -237,7 +237,9 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     // no votes in this loop: a lane records what concerns ITS particle / proposal (the relations are symmetric),
                     // and the rare hit masks go to the 32x32 table with an atomicOr on the trial's row word
                     const float MGs = 12582912.f;
-                    nscr += (unsigned)((te - (tb & ~1) + 1) & ~1);
+                    const int t_first = tb & ~1, n_scr = (te - t_first + 1) & ~1;   // the loop below visits trials t_first .. t_first + n_scr - 1
+                    nscr += (unsigned)n_scr;
+                    unsigned in_sr = 0, pp_sr = 0;      // my_in / my_pp as shift registers: one funnel shift per trial, placed after the loop
                     const float2 MG2 = make_float2(MGs, MGs), rc2 = make_float2(sc.rc2s, sc.rc2s);
                     const float2 stx2 = make_float2(st_x, st_x), sty2 = make_float2(st_y, st_y), stz2 = make_float2(st_z, st_z);
                     for (int t2 = tb & ~1; t2 < te; t2 += 2) {
@@ -250,15 +252,20 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                             const int t = t2 + h;
                             const unsigned m = screen_slots_sgn<K, PZ>(sc, h ? ax2.y : ax2.x, h ? ay2.y : ay2.x, h ? az2.y : az2.x, q) & validmask & ~((lane == t) ? 1u : 0u);
                             if (m) { hm[t * 32 + lane] = (HM)m; atomicOr(hbrow + t, 1u << lane); }
-                            my_in |= (m & 1u) << t;
+                            in_sr = __funnelshift_r(in_sr, m, 1);           // bit 0 of m enters at the top
                         }
                         // proposal against proposal, both trials of the iteration in one packed pass
                         float2 dx = sub2(ax2, stx2), dy = sub2(ay2, sty2), dz = sub2(az2, stz2);
                         dx = sub2(dx, sub2(add2(dx, MG2), MG2));
                         dy = sub2(dy, sub2(add2(dy, MG2), MG2));
                         if (PZ) dz = fma2(sub2(add2(mul2(dz, make_float2(sc.inv_zper, sc.inv_zper)), MG2), MG2), make_float2(-sc.zper, -sc.zper), dz);
-                        const float2 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-                        my_pp |= (((r2.x < rc2.x) ? 1u : 0u) | ((r2.y < rc2.y) ? 2u : 0u)) << t2;
+                        const float2 dd = sub2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), rc2);   // sign = inside, as in screen_slots_sgn
+                        pp_sr = __funnelshift_l(__float_as_uint(dd.x), pp_sr, 1);
+                        pp_sr = __funnelshift_l(__float_as_uint(dd.y), pp_sr, 1);
+                    }
+                    if (n_scr > 0) {
+                        my_in = (in_sr >> (32 - n_scr)) << t_first;                  // the first trial visited was shifted down the farthest
+                        my_pp = (__brev(pp_sr) >> (32 - n_scr)) << t_first;          // ... and up the farthest here
                     }
                     my_pp &= ~(1u << lane);
                     __syncwarp();
