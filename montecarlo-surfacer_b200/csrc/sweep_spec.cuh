@@ -337,21 +337,26 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                 // before f are committed together by their owner lanes, then f is handled alone.
                 const bool lonely = mine && !p_bad && p_np == 0 && nb0 == 0;
                 const unsigned lowmask = (1u << lane) - 1u;
+                // what does not change during the epochs is voted ONCE: the loop below then needs one vote per epoch (which
+                // pending trials an accepted or still open earlier trial interferes with) and one shuffle
+                const unsigned mineb = __ballot_sync(FULL, mine);
+                const unsigned accb = __ballot_sync(FULL, mine && p_acc);
+                const unsigned badb = __ballot_sync(FULL, mine && (lite || p_bad));
+                const unsigned serialb = accb & ~__ballot_sync(FULL, lonely);      // accepted, but with partners: the owner commits it alone
                 int cur = tb;
                 while (cur < te) {
-                    const bool pending = mine && lane >= cur;
+                    const unsigned pendb = mineb & ~((1u << cur) - 1u);
+                    const bool pending = (pendb >> lane) & 1u;
                     const unsigned X = my_in | my_po | my_pp;
-                    const bool isdirty = (dirty >> lane) & 1u;
                     // trials whose particle may still move in this segment (decision open, or accepted)
-                    const unsigned move = __ballot_sync(FULL, pending && (lite || p_bad || isdirty || p_acc));
+                    const unsigned move = pendb & (badb | dirty | accb);
                     if (move == 0u) {                    // the rest are rejections; void only if an ACCEPTED trial interferes
                         if (__ballot_sync(FULL, pending && (X & A) != 0u) == 0u) break;
                     }
-                    const bool hard = pending && (lite || p_bad || isdirty || (X & (A | (move & lowmask))) != 0u || (p_acc && !lonely));
-                    const unsigned hardb = __ballot_sync(FULL, hard);
+                    const unsigned hardb = __ballot_sync(FULL, pending && (X & (A | (move & lowmask))) != 0u) | (pendb & (badb | dirty | serialb));
                     const int f = hardb ? __ffs(hardb) - 1 : 32;
-                    const bool commit = pending && lane < f && p_acc;      // lonely, and nothing before it in the segment interferes
-                    const unsigned cm = __ballot_sync(FULL, commit);
+                    const unsigned cm = pendb & accb & (hardb ? ((1u << f) - 1u) : 0xffffffffu);   // lonely, and nothing before them in the segment interferes
+                    const bool commit = (cm >> lane) & 1u;
                     if (cm) {
                         if (commit) {
                             s.x[nl] = p_qx; s.y[nl] = p_qy; s.z[nl] = p_qz;
@@ -368,12 +373,12 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     const int t = f;
                     cur = t + 1;
                     // with the epoch's commits known: does trial t's speculation stand?
-                    const unsigned confb = __ballot_sync(FULL, pending && (lite || p_bad || isdirty || (X & A) != 0u));
-                    if (!((confb >> t) & 1u) && !((__ballot_sync(FULL, p_acc) >> t) & 1u)) { SMCB_ST(8, 1); continue; }    // a valid rejection
+                    const bool conf_t = (((badb | dirty) >> t) & 1u) || (__shfl_sync(FULL, X, t) & A) != 0u;
+                    if (!conf_t && !((accb >> t) & 1u)) { SMCB_ST(8, 1); continue; }    // a valid rejection
                     const int n = 32 * slot + t;
                     const unsigned okmask = validmask & ~((lane == t) ? 1u : 0u);
                     const int nbm = s.nb[n];
-                    if (!((confb >> t) & 1u)) {
+                    if (!conf_t) {
                         // ---- the speculation of trial t stands and it accepts: its owner commits it
                         SMCB_ST(2, 1); SMCB_ST(10, __shfl_sync(FULL, pj, t) >= 0 ? 1 : 0);
                         if (nbm) {                       // the old partners forget this particle
