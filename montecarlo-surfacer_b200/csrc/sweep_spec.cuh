@@ -33,6 +33,7 @@
 
 namespace smcb {
 
+constexpr unsigned short kNoP1 = 0xffffu;
 template <int K> struct HitMaskT { typedef unsigned char type; };
 template <> struct HitMaskT<16> { typedef unsigned short type; };
 
@@ -41,7 +42,7 @@ struct SpecSmem {
     static constexpr int NS = 32 * K;
     static __host__ __device__ size_t bytes(int MMpad)
     {
-        return ChainSmem::bytes(NS, MMpad) + (size_t)32 * 32 * sizeof(typename HitMaskT<K>::type) + 32 * sizeof(unsigned);
+        return ChainSmem::bytes(NS, MMpad) + (size_t)32 * 32 * sizeof(typename HitMaskT<K>::type) + 32 * sizeof(unsigned) + (size_t)NS * sizeof(unsigned short);
     }
 };
 
@@ -91,6 +92,9 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
     s.carve(sm, 32 * K, MMpad);
     unsigned *hbrow = reinterpret_cast<unsigned *>(s.site + 4 * MMpad);   // [trial]: which lanes hold hits for the trial's proposal
     HM *hm = reinterpret_cast<HM *>(hbrow + 32);               // [trial][lane]: the lane's hit mask for the trial's proposal
+    // [particle]: WHO the partner is while the particle has exactly one (kNoP1: not known) - an accepted move of such a
+    // particle then corrects that partner's caches from the owner lane, without screening the old position again
+    unsigned short *p1 = reinterpret_cast<unsigned short *>(hm + 32 * 32);
     const smcb_chain_params &cp = chain_params(d, chain);
     const Box b = make_box(cp, d.M, d.step_scale);
     const double *W = d.W + (size_t)cp.wall * 2 * MM;
@@ -129,6 +133,8 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
         Erebuilt += U - 0.5 * Up;                    // energy(R) + wallsEnergy(R), SMC.c:48
         const int cntn = __reduce_add_sync(FULL, __popc(in));
         if (lane == 0) { s.ce[n] = U; s.cfx[n] = Fx; s.cfy[n] = Fy; s.cfz[n] = Fz; s.nb[n] = (unsigned short)cntn; }
+        if (cntn == 1) { if (in) p1[n] = (unsigned short)(lane + 32 * (__ffs(in) - 1)); }
+        else if (lane == 0) p1[n] = kNoP1;
     }
     __syncwarp();
 
@@ -325,7 +331,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                         double et, hx, hy, hz;
                         if (pair_exact(b, px, py, pz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
                             s.ce[j] -= 4.0 * et; s.cfx[j] += hx; s.cfy[j] += hy; s.cfz[j] += hz;
-                            s.nb[j] -= 1;
+                            s.nb[j] -= 1; p1[j] = kNoP1;          // whoever is left, it is not recorded
                             touched |= (k == 0);
                         }
                     }
@@ -381,7 +387,18 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                     if (!conf_t) {
                         // ---- the speculation of trial t stands and it accepts: its owner commits it
                         SMCB_ST(2, 1); SMCB_ST(10, __shfl_sync(FULL, pj, t) >= 0 ? 1 : 0);
-                        if (nbm) {                       // the old partners forget this particle
+                        const int p1n = p1[n];
+                        if (nbm == 1 && p1n != kNoP1) {  // the one old partner is on record: the owner lane corrects it
+                            SMCB_ST(9, 1);
+                            if (lane == t) {
+                                double et, hx, hy, hz;
+                                if (pair_exact(b, s.x[n], s.y[n], s.z[n], s.x[p1n], s.y[p1n], s.z[p1n], et, hx, hy, hz)) {
+                                    s.ce[p1n] -= 4.0 * et; s.cfx[p1n] += hx; s.cfy[p1n] += hy; s.cfz[p1n] += hz;
+                                    s.nb[p1n] -= 1; p1[p1n] = kNoP1;
+                                }
+                            }
+                            if ((p1n >> 5) == slot) dirty |= 1u << (p1n & 31);
+                        } else if (nbm) {                // the old partners forget this particle
                             SMCB_ST(9, 1);
                             __syncwarp();
                             dirty |= __ballot_sync(FULL, drop_old_partners(n, okmask));
@@ -390,7 +407,8 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                         if (lane == t) {
                             if (p_np == 1) {             // the one new partner gains the pair terms (force on j from n = -g d)
                                 s.ce[pj] += 4.0 * pe; s.cfx[pj] -= pgx; s.cfy[pj] -= pgy; s.cfz[pj] -= pgz;
-                                s.nb[pj] += 1;
+                                const unsigned short c = s.nb[pj] + 1;
+                                s.nb[pj] = c; p1[pj] = (c == 1) ? (unsigned short)n : kNoP1;
                             } else if (p_np > 1) {       // several: the lane holds their SUMS; each one's terms are formed again
                                 unsigned hb = my_hb;
                                 while (hb) {
@@ -406,14 +424,15 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                                         double et, hx, hy, hz;
                                         if (pair_exact(b, p_qx, p_qy, p_qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz)) {
                                             s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
-                                            s.nb[j] += 1;
+                                            const unsigned short c = s.nb[j] + 1;
+                                            s.nb[j] = c; p1[j] = (c == 1) ? (unsigned short)n : kNoP1;
                                         }
                                     }
                                 }
                             }
                             s.x[n] = p_qx; s.y[n] = p_qy; s.z[n] = p_qz;
                             s.ce[n] = 4.0 * (pe + p_ew); s.cfx[n] = pgx; s.cfy[n] = pgy; s.cfz[n] = pgz + p_fz;
-                            s.nb[n] = (unsigned short)p_np;
+                            s.nb[n] = (unsigned short)p_np; p1[n] = (p_np == 1) ? (unsigned short)pj : kNoP1;
                             q.set(0, st_x, st_y, st_z);
                             dE += p_dU;                 // SMC.c:341, summed per lane, reduced at the end of the sweep
                         }
@@ -518,7 +537,7 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                         // partners lose the old pair terms and gain the new ones (force on j from n = -g d)
                         bool touched = false;           // physical slot 0 = the slot being visited: its speculation is void
                         if (nbm) touched = drop_old_partners(n, okmask);
-                        int nbn = 0;
+                        int nbn = 0, j1 = kNoP1;
                         if (work) {
                             unsigned hn = in_new;
                             const bool single = __popc(in_new) == 1 && !(near && lane < MM);   // le.. are that one pair's terms
@@ -529,17 +548,20 @@ __device__ __forceinline__ void sweep_spec_body(const DevChains &d, const SweepA
                                 double et = le, hx = lx, hy = ly, hz = lz;
                                 if (!single) pair_exact(b, qx, qy, qz, s.x[j], s.y[j], s.z[j], et, hx, hy, hz);
                                 s.ce[j] += 4.0 * et; s.cfx[j] -= hx; s.cfy[j] -= hy; s.cfz[j] -= hz;
-                                s.nb[j] += 1;
+                                const unsigned short c = s.nb[j] + 1;
+                                s.nb[j] = c; p1[j] = (c == 1) ? (unsigned short)n : kNoP1;
                                 touched |= (k == 0);
+                                j1 = j;
                             }
                             nbn = __reduce_add_sync(FULL, __popc(in_new));
+                            if (nbn == 1) j1 = __shfl_sync(FULL, j1, __ffs(__ballot_sync(FULL, in_new != 0)) - 1);   // the one new partner, for the record
                         }
                         dirty |= __ballot_sync(FULL, touched);
                         __syncwarp();                    // partner updates read the old position of n: order before overwriting it
                         if (lane == t) {                 // the owner: physical slot 0 is the visited slot
                             s.x[n] = qx; s.y[n] = qy; s.z[n] = qz;
                             s.ce[n] = Un; s.cfx[n] = Fnx; s.cfy[n] = Fny; s.cfz[n] = Fnz;
-                            s.nb[n] = (unsigned short)nbn;
+                            s.nb[n] = (unsigned short)nbn; p1[n] = (nbn == 1) ? (unsigned short)j1 : kNoP1;
                             q.set(0, qsx, qsy, qsz);
                         }
                         E += Un - Um;                   // SMC.c:341
