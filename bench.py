@@ -46,8 +46,8 @@ FLOPS_PAIR, FLOPS_INCUT = 17.0, 16.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="smcb200", choices=["smcb200", "reference"])
     ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default 8192; largeN: 256/world)")
     ap.add_argument("--sweeps-per-step", type=int, default=40)
