@@ -11,7 +11,9 @@
 //   phase 2  the 32 proposals are screened against all K slots in one pipelined loop (independent iterations, two
 //            trials in flight).  Lane t keeps, for ITS trial: which lanes found hits (the hit masks go to a 32x32
 //            table in shared memory), which of the segment's own particles are in range of its proposal (po), and
-//            which of the other PROPOSALS are (pp, from a proposal-against-proposal test in the same loop)
+//            which of the other PROPOSALS are (pp, from a proposal-against-proposal test in the same loop, both trials
+//            of an iteration in one packed pass).  Hit bits are the SIGN of r2 - rc2 moved into the mask by funnel
+//            shifts (screen_slots_sgn); `in` and `pp` are collected in shift registers, one funnel shift per trial
 //   phase 3  lane t evaluates the exact FP64 pair terms of its own trial's partners (0-1 of them in the gas: a
 //            short divergent loop; it keeps their SUMS, up to SMCB_SPEC_MAXPARTNERS partners), adds the flat wall,
 //            and decides its trial completely (SMC.c:319-335)
@@ -21,7 +23,10 @@
 //            inputs were changed by an earlier accepted trial of the segment - its cached force (dirty), or the set
 //            of particles in range of its proposal ((pp | po) & accepted) - or that is near the surface or has
 //            more partners than that, is redone on the warp-wide general path of k_sweep_cached.  Rejected trials with
-//            valid speculation cost nothing in phase 4.
+//            valid speculation cost nothing in phase 4.  What cannot change during the epochs (mine, accepted, bad,
+//            lonely) is voted once per segment: an epoch is one vote and one shuffle.  A molecule with exactly one
+//            partner keeps a record of who it is (p1[]), so its accepted move corrects that partner from the owner
+//            lane instead of screening the old position again.
 // A trial's speculation is valid exactly when nothing it read has changed since the start of the segment, so the
 // results are those of the sequential sweep (tests: accept flags identical to the oracle's, positions and energies
 // within 1e-12 teacher-forced; cache consistency after many sweeps).
